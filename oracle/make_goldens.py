@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by EXECUTING THE UNMODIFIED REFERENCE in the build container.
+
+Run here (``python oracle/make_goldens.py``); needs /root/reference, which does not exist on the
+GPU box - that is why the outputs are committed.  Nothing is copied from the reference: modules are
+imported from where they lie and only their numerical outputs are stored.
+
+  hifigan_mini.npz     reference hifigan/models.py:Generator, mini config (C0=32), seeded weights
+                       stored in the file, ResBlock1; loud input
+  hifigan_mini_rb2.npz same with resblock "2" (config_v3-style, hifigan/models.py:63-68)
+  hifigan_neb.npz      reference Generator + shipped data/models/vocoder/neb-noft/g_00600000
+                       (weights NOT stored - staged by oracle/stage_weights.py), F=24
+  heads.npz            cube/networks/loss.py MULAW/RAW/MOL/Gaussian encode/decode/sample
+  upsample2.npz        cube/networks/modules.py UpsampleNet2/R/I (+ teacher upsample weights)
+  clarinet_regress.npz NOT reference-derived (no forward code in the reference): regression
+                       snapshot of oracle/clarinet_ref.py with the shipped checkpoints
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("CUBE_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+sys.path.insert(0, os.path.dirname(HERE))
+
+
+def _stub_matplotlib():
+    # hifigan/utils.py:3,6-7 imports matplotlib (not installed); the generator never uses it
+    m = types.ModuleType("matplotlib")
+    m.use = lambda *a, **k: None
+    p = types.ModuleType("matplotlib.pylab")
+    m.pylab = p
+    sys.modules.setdefault("matplotlib", m)
+    sys.modules.setdefault("matplotlib.pylab", p)
+
+
+def import_reference_hifigan():
+    _stub_matplotlib()
+    sys.path.insert(0, os.path.join(REF, "hifigan"))
+    import models as ref_models  # noqa  (reference hifigan/models.py)
+    from env import AttrDict      # noqa  (reference hifigan/env.py)
+    return ref_models, AttrDict
+
+
+def main():
+    from oracle import hifigan_ref as H, clarinet_ref as C, heads_ref as W
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref_models, AttrDict = import_reference_hifigan()
+
+    # ---------------- Path H, mini configs with stored weights ----------------
+    for tag, resblock, dil, gs in (("hifigan_mini", "1", [[1, 3, 5]] * 3, 0.42),
+                                   ("hifigan_mini_rb2", "2", [[1, 3]] * 3, 0.5)):
+        cfg = dict(H.CONFIG_V1, upsample_initial_channel=32, resblock=resblock, resblock_dilation_sizes=dil)
+        sd = H.random_state_dict(cfg, seed=11, std=0.3, g_scale=gs)
+        gen = ref_models.Generator(AttrDict(cfg)).eval()
+        gen.load_state_dict(sd, strict=True)
+        mel = H.synthetic_mel(2, 13, seed=5, level=0.0)
+        with torch.no_grad():
+            y = gen(mel)
+        print(tag, tuple(y.shape), "peak", float(y.abs().max()))
+        np.savez_compressed(os.path.join(OUT, tag + ".npz"), mel=mel.numpy(), wav=y.numpy(),
+                            cfg=np.array(repr(cfg)), **{"w:" + k: v.numpy() for k, v in sd.items()})
+
+    # ---------------- Path H, shipped generator ----------------
+    ck = torch.load(os.path.join(REF, "data/models/vocoder/neb-noft/g_00600000"), map_location="cpu",
+                    weights_only=False)["generator"]
+    cfg = H.load_config(os.path.join(REF, "data/models/vocoder/neb-noft/config.json"))
+    gen = ref_models.Generator(AttrDict(cfg)).eval()
+    gen.load_state_dict(ck, strict=True)
+    mel = H.synthetic_mel(2, 24, seed=1237, level=0.0)
+    with torch.no_grad():
+        y_wn = gen(mel)                 # weight-norm live (the cube/api.py path)
+        gen.remove_weight_norm()        # the cube/io_utils/runtime.py:53 path
+        y = gen(mel)
+    print("hifigan_neb", tuple(y.shape), "peak", float(y.abs().max()), "wn-vs-folded", float((y - y_wn).abs().max()))
+    np.savez_compressed(os.path.join(OUT, "hifigan_neb.npz"), mel=mel.numpy(), wav=y.numpy(),
+                        wav_int16=(y.numpy().squeeze(1) * 32767).astype(np.int16))
+
+    # ---------------- heads ----------------
+    sys.path.insert(0, REF)
+    from cube.networks import loss as ref_loss  # reference cube/networks/loss.py, unmodified
+    mu = ref_loss.MULAWOutput()
+    raw = ref_loss.RAWOutput()
+    mol = ref_loss.MOLOutput()
+    gau = ref_loss.GaussianOutput()
+    g = torch.Generator().manual_seed(77)
+    x = torch.cat([torch.linspace(-1, 1, 20001), torch.rand(20000, generator=g) * 2 - 1,
+                   torch.tensor([1.0, 0.9, 0.0, -0.9, -1.0, 1.5, -1.5, 1e-8, -1e-8])])
+    enc = mu.encode(x)
+    table = mu.decode(torch.arange(256))
+    edges = W.mulaw_encode_edges(encode=mu.encode)
+    # neighbours of every edge (the hard cases)
+    nb = np.concatenate([np.nextafter(edges, -np.inf, dtype=np.float32), edges,
+                         np.nextafter(edges, np.inf, dtype=np.float32)])
+    enc_nb = mu.encode(torch.from_numpy(nb))
+    y = torch.randn(3, 50, 30, generator=g)
+    y[:, :, 20:] = y[:, :, 20:] * 0.5 - 3.0
+    torch.manual_seed(4242)
+    x_mol = mol.sample(y)
+    torch.manual_seed(4242)
+    u_mix = torch.empty(3, 50, 10).uniform_(1e-5, 1 - 1e-5)
+    u_x = torch.empty(3, 50).uniform_(1e-5, 1.0 - 1e-5)
+    yh = torch.randn(3, 50, 2, generator=g)
+    yh[:, :, 1] = yh[:, :, 1] * 0.3 - 2.0
+    torch.manual_seed(99)
+    x_g = gau.sample(yh)
+    torch.manual_seed(99)
+    eps = torch.randn(3, 50, 1)
+    xr = torch.rand(5000, generator=g) * 2.4 - 1.2
+    np.savez_compressed(
+        os.path.join(OUT, "heads.npz"), mulaw_x=x.numpy(), mulaw_q=enc.numpy(), mulaw_table=table.numpy(),
+        mulaw_edges=edges, mulaw_nb_x=nb, mulaw_nb_q=enc_nb.numpy(),
+        raw_x=xr.numpy(), raw_q=raw.encode(xr).numpy(), raw_table=raw.decode(torch.arange(256)).numpy(),
+        mol_y=y.numpy(), mol_u_mix=u_mix.numpy(), mol_u_x=u_x.numpy(), mol_x=x_mol.numpy(),
+        gau_y=yh.numpy(), gau_eps=eps.squeeze(2).numpy(), gau_x=x_g.reshape(3, 50).numpy())
+    print("heads: KAT", mu.encode(np.array([1, 0.9, 0, -0.9, -1])), "edges", edges[:3], edges[-3:])
+
+    # ---------------- upsamplers ----------------
+    from cube.networks import modules as ref_mod  # reference cube/networks/modules.py, unmodified
+    tsd = torch.load(os.path.join(REF, "data/models/nn_vocoder.network"), map_location="cpu", weights_only=False)
+    ssd = torch.load(os.path.join(REF, "data/models/pnn_vocoder.network"), map_location="cpu", weights_only=False)
+    C.check_state_dict(tsd, "teacher")
+    C.check_state_dict(ssd, "student")
+    up = ref_mod.UpsampleNet2([16, 16])
+    up.load_state_dict({k.replace("upsample_conv.", "_upsample_conv."): v for k, v in tsd.items()
+                        if k.startswith("upsample_conv.")}, strict=True)
+    mel01 = C.synthetic_mel01(1, 5, seed=3)
+    with torch.no_grad():
+        c_up = up(mel01)
+        r3 = ref_mod.UpsampleNetR(3)(mel01[:, :4])
+        i3 = ref_mod.UpsampleNetI(3)(mel01[:, :4])
+    np.savez_compressed(os.path.join(OUT, "upsample2.npz"), mel=mel01.numpy(), c_up=c_up.numpy(),
+                        rep3=r3.numpy(), lin3=i3.numpy(),
+                        **{"w:" + k: v.numpy() for k, v in tsd.items() if k.startswith("upsample_conv.")})
+    print("upsample2", tuple(c_up.shape))
+
+    # ---------------- ClariNet regression snapshot (oracle-derived, NOT reference-derived) -------
+    melc = C.synthetic_mel01(1, 6, seed=8)
+    z = torch.randn(1, 1, 6 * 256, generator=torch.Generator().manual_seed(9))
+    xs = C.vocode_student(ssd, tsd, melc, z)
+    np.savez_compressed(os.path.join(OUT, "clarinet_regress.npz"), mel=melc.numpy(), z=z.numpy(), wav=xs.numpy())
+    print("clarinet_regress", tuple(xs.shape), "std", float(xs.std()), "peak", float(xs.abs().max()))
+
+
+if __name__ == "__main__":
+    main()
