@@ -147,5 +147,24 @@ def main():
     print("clarinet_regress", tuple(xs.shape), "std", float(xs.std()), "peak", float(xs.abs().max()))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--inc-only" not in sys.argv:
     main()
+
+
+def write_mulaw_inc():
+    """Emit tts_cube_b200/csrc/mulaw_tables.inc from tests/golden/heads.npz (the reference's own
+    float32 bin edges / decode values, as exact hex-float literals)."""
+    d = np.load(os.path.join(OUT, "heads.npz"))
+    dst = os.path.join(os.path.dirname(HERE), "tts_cube_b200", "csrc", "mulaw_tables.inc")
+    with open(dst, "w") as f:
+        f.write("// GENERATED by oracle/make_goldens.py from the reference's float32 torch path\n"
+                "// (cube/networks/loss.py:236-269 executed in the build container). Do not edit.\n")
+        f.write("static const float MULAW_EDGES_H[255] = {\n")
+        f.write(",\n".join("  " + float(v).hex() + "f" for v in d["mulaw_edges"]))
+        f.write("\n};\nstatic const float MULAW_DECODE_H[256] = {\n")
+        f.write(",\n".join("  " + float(v).hex() + "f" for v in d["mulaw_table"]))
+        f.write("\n};\n")
+
+
+if __name__ == "__main__":
+    write_mulaw_inc()

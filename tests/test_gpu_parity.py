@@ -1,0 +1,291 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference-generated golden
+fixtures.  Tolerance for waveforms: 1e-3 max-abs on fp32 samples (BASELINE.json north_star); integer
+work (mu-law codes, int16 audio away from rounding ties) is bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_cfg, golden_weights, load_golden
+from oracle import clarinet_ref as C, heads_ref as W, hifigan_ref as H
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _gen(cfg, sd, dev):
+    import tts_cube_b200 as cube
+    g = cube.CubeGenerator(cfg).to(dev)
+    g.load_state_dict(sd)
+    return g.eval()
+
+
+# ------------------------------------------------ Path H ------------------------------------------------
+@pytest.mark.parametrize("name", ["hifigan_mini.npz", "hifigan_mini_rb2.npz"])
+def test_hifigan_golden_mini(dev, name):
+    d = load_golden(name)
+    g = _gen(golden_cfg(d), golden_weights(d), dev)
+    with torch.no_grad():
+        y = g(torch.from_numpy(d["mel"]).to(dev)).cpu().numpy()
+    assert y.shape == d["wav"].shape
+    err = float(np.abs(y - d["wav"]).max())
+    assert err <= TOL, err
+    assert err <= 2e-5, f"fp32 SIMT path should sit near fp32 round-off, got {err}"
+
+
+def test_hifigan_golden_trained(dev, neb):
+    sd, cfg = neb
+    d = load_golden("hifigan_neb.npz")
+    g = _gen(cfg, sd, dev)
+    with torch.no_grad():
+        wav, w16 = g.forward_int16(torch.from_numpy(d["mel"]).to(dev))
+    err = float(np.abs(wav.cpu().numpy() - d["wav"]).max())
+    assert err <= TOL, err
+    # int16 epilogue: identical wherever the float product is not within fp32 noise of an integer
+    ref16 = d["wav_int16"].astype(np.int32)
+    got16 = w16.cpu().numpy().astype(np.int32)
+    assert np.abs(got16 - ref16).max() <= 1
+    frac = np.abs(d["wav"].squeeze(1) * 32767 - np.round(d["wav"].squeeze(1) * 32767))
+    safe = frac > 32767 * 4 * err + 1e-3
+    assert np.array_equal(got16[~(~safe)], ref16[safe]) if safe.any() else True
+    # and exactly int16(wav*32767) of the wav it returned (cube/api.py:65)
+    assert torch.equal(w16.cpu(), H.wav_to_int16(wav.cpu()).squeeze(1))
+
+
+@pytest.mark.parametrize("level", [-5.0, 0.0, 1.0])
+def test_hifigan_trained_loudness_sweep(dev, neb, level):
+    sd, cfg = neb
+    mel = H.synthetic_mel(2, 40, seed=1237 + int(level), level=level)
+    ref = H.generator_forward(sd, cfg, mel)
+    g = _gen(cfg, sd, dev)
+    with torch.no_grad():
+        y = g(mel.to(dev)).cpu()
+    assert float((y - ref).abs().max()) <= TOL
+    if level >= 0:
+        assert float(ref.abs().max()) > 0.5  # loud: the tolerance check means something
+
+
+def test_hifigan_config_v1_random_weights_ragged(dev):
+    cfg = dict(H.CONFIG_V1, upsample_initial_channel=64)
+    sd = H.random_state_dict(cfg, seed=21, std=0.3, g_scale=0.36)
+    mel = H.synthetic_mel(3, 21, seed=8)
+    frames = [21, 1, 12]
+    ref = H.generator_forward_ragged(sd, cfg, mel, frames)
+    assert float(ref.abs().max()) > 0.05
+    mel_pad = mel.clone()
+    mel_pad[1, :, 1:] = -5.0   # VocoderCollate pads with -5 (cube/io_utils/io_vocoder.py:86): must be ignored
+    mel_pad[2, :, 12:] = 7.0
+    g = _gen(cfg, sd, dev)
+    with torch.no_grad():
+        y = g(mel_pad.to(dev), n_frames=frames).cpu()
+    assert y.shape == ref.shape
+    assert float((y - ref).abs().max()) <= TOL
+    for b, f in enumerate(frames):
+        assert float(y[b, 0, H.out_len(cfg, f):].abs().max()) == 0.0
+
+
+def test_hifigan_edge_cases(dev):
+    import tts_cube_b200 as cube
+    cfg = dict(H.CONFIG_V1, upsample_initial_channel=32)
+    sd = H.random_state_dict(cfg, seed=11, std=0.3, g_scale=0.42)
+    g = _gen(cfg, sd, dev)
+    with torch.no_grad():
+        one = g(H.synthetic_mel(1, 1, seed=1).to(dev))        # a single frame
+        assert one.shape == (1, 1, H.out_len(cfg, 1))
+        ref = H.generator_forward(sd, cfg, H.synthetic_mel(1, 1, seed=1))
+        assert float((one.cpu() - ref).abs().max()) <= TOL
+        z = g(H.synthetic_mel(2, 5, seed=2).to(dev), n_frames=[0, 5]).cpu()  # an empty utterance in a batch
+        assert float(z[0].abs().max()) == 0.0
+        with pytest.raises(cube.CubeVocError):
+            g(torch.zeros(1, 80, 4))                             # CPU tensor: no fallback
+        with pytest.raises(cube.CubeVocError):
+            g(torch.zeros(1, 80, 4, device=dev), n_frames=[9])   # n_frames > Fmax
+    bad = cube.CubeGenerator(cfg).to(dev)
+    sd2 = dict(sd)
+    del sd2["ups.1.bias"]
+    bad.load_state_dict(sd2)
+    with pytest.raises(cube.CubeVocError, match="ups.1.bias"):
+        bad(torch.zeros(1, 80, 4, device=dev))                  # strict load like the reference
+    x = torch.zeros(1, 80, 4, device=dev, requires_grad=True)
+    with pytest.raises(cube.CubeVocError):
+        g(x)                                                    # inference only
+
+
+def test_hifigan_host_call_matches_device_call(dev):
+    cfg = dict(H.CONFIG_V1, upsample_initial_channel=32)
+    sd = H.random_state_dict(cfg, seed=11, std=0.3, g_scale=0.42)
+    g = _gen(cfg, sd, dev)
+    mel = H.synthetic_mel(2, 17, seed=3)
+    with torch.no_grad():
+        a = g(mel.to(dev)).cpu().squeeze(1)
+    b = g.forward_host(mel.pin_memory())
+    assert torch.equal(a, b)
+    c = g.forward_host(mel, int16=True)
+    assert torch.equal(c, H.wav_to_int16(a))
+
+
+def test_hifigan_full_size_properties(dev, neb):
+    """BASELINE config 3 shape (10 s utterances) through size-independent properties: batch items are
+    independent and a long utterance equals the same utterance inside a padded batch."""
+    sd, cfg = neb
+    g = _gen(cfg, sd, dev)
+    F = 919
+    mel = H.synthetic_mel(2, F, seed=77)
+    with torch.no_grad():
+        y2 = g(mel.to(dev))
+        y1 = g(mel[1:2].to(dev))
+        short = g(torch.cat([mel[:1], mel[:1]], 0).to(dev), n_frames=[F, 300])
+    assert y2.shape == (2, 1, H.out_len(cfg, F))
+    assert torch.equal(y2[1], y1[0])                       # no cross-utterance leakage, deterministic
+    assert torch.equal(short[0], y2[0])
+    alone = g(mel[:1, :, :300].contiguous().to(dev))
+    assert torch.equal(short[1, :, : alone.shape[2]], alone[0])
+    assert float(y2.abs().max()) > 0.5 and bool(torch.isfinite(y2).all())
+    # oracle spot-check on the first second only would need the full receptive field; instead check the
+    # head of the utterance against the oracle run on a prefix long enough to cover it
+    pre = H.generator_forward(sd, cfg, mel[:1, :, :64])
+    n = H.out_len(cfg, 40)
+    assert float((y2[0, 0, :n].cpu() - pre[0, 0, :n]).abs().max()) <= TOL
+
+
+# ------------------------------------------------ Path C ------------------------------------------------
+def _student(ssd, tsd, dev):
+    import tts_cube_b200 as cube
+    return cube.ParallelWaveNetVocoder(ssd, tsd).to(dev).eval()
+
+
+def test_upsample2_golden(dev):
+    d = load_golden("upsample2.npz")
+    tsd = golden_weights(d)
+    ssd = C.random_state_dict("student", 5, blocks=[1, 1])
+    v = _student(ssd, tsd, dev)
+    mel = torch.from_numpy(d["mel"])
+    T = mel.shape[2] * 256
+    with torch.no_grad():
+        v(mel.to(dev), torch.zeros(1, 1, T, device=dev))
+    c = v.conditioning(1, T).cpu().numpy()
+    assert float(np.abs(c - d["c_up"]).max()) <= 1e-5
+
+
+def test_student_small_random_weights(dev):
+    ssd, tsd = C.random_state_dict("student", 3, blocks=[7, 2, 1, 3]), C.random_state_dict("teacher", 4, blocks=[1])
+    mel = C.synthetic_mel01(2, 5, seed=2)
+    z = torch.randn(2, 1, 5 * 256, generator=torch.Generator().manual_seed(1))
+    ref = C.vocode_student(ssd, tsd, mel, z)
+    v = _student(ssd, tsd, dev)
+    with torch.no_grad():
+        x = v(mel.to(dev), z.to(dev)).cpu()
+    assert float(ref.abs().max()) > 0.05
+    assert float((x - ref).abs().max()) <= TOL
+    assert float((x - ref).abs().max()) <= 5e-5
+
+
+def test_student_shipped_weights(dev, clarinet_weights):
+    ssd, tsd, trained = clarinet_weights
+    mel = C.synthetic_mel01(2, 8, seed=8)
+    z = torch.randn(2, 1, 8 * 256, generator=torch.Generator().manual_seed(9))
+    ref = C.vocode_student(ssd, tsd, mel, z)
+    v = _student(ssd, tsd, dev)
+    with torch.no_grad():
+        x = v(mel.to(dev), z.to(dev)).cpu()
+    assert float(ref.abs().max()) > 0.1
+    assert float((x - ref).abs().max()) <= TOL
+    if trained:
+        d = load_golden("clarinet_regress.npz")
+        with torch.no_grad():
+            xr = v(torch.from_numpy(d["mel"]).to(dev), torch.from_numpy(d["z"]).to(dev)).cpu().numpy()
+        assert float(np.abs(xr - d["wav"]).max()) <= TOL
+
+
+def test_student_ragged_and_causal(dev):
+    ssd, tsd = C.random_state_dict("student", 3, blocks=[6, 1, 1, 2]), C.random_state_dict("teacher", 4, blocks=[1])
+    mel = C.synthetic_mel01(2, 6, seed=12)
+    z = torch.randn(2, 1, 6 * 256, generator=torch.Generator().manual_seed(3))
+    v = _student(ssd, tsd, dev)
+    mel_pad = mel.clone()
+    mel_pad[1, :, 4:] = 9.0
+    with torch.no_grad():
+        x = v(mel_pad.to(dev), z.to(dev), n_frames=[6, 4]).cpu()
+    alone = C.vocode_student(ssd, tsd, mel[1:2, :, :4], z[1:2, :, : 4 * 256])
+    assert float((x[1, :, : 4 * 256] - alone[0]).abs().max()) <= TOL
+    assert float(x[1, :, 4 * 256:].abs().max()) == 0.0
+    full = C.vocode_student(ssd, tsd, mel[:1], z[:1])
+    assert float((x[0] - full[0]).abs().max()) <= TOL
+    # host-buffer call == device call
+    with torch.no_grad():
+        d_ = v(mel.to(dev), z.to(dev)).cpu().squeeze(1)
+    assert torch.equal(v.forward_host(mel.pin_memory(), z.pin_memory()), d_)
+
+
+def test_student_full_length_properties(dev):
+    """Config-2 length (10 s, T=220672) with a shallow student: finite, deterministic, causal (a change
+    of z at sample s never alters samples < s) and batch items independent."""
+    ssd, tsd = C.random_state_dict("student", 3, blocks=[6, 1]), C.random_state_dict("teacher", 4, blocks=[1])
+    F = 862
+    mel = C.synthetic_mel01(2, F, seed=5)
+    g = torch.Generator().manual_seed(11)
+    z = torch.randn(2, 1, F * 256, generator=g)
+    v = _student(ssd, tsd, dev)
+    with torch.no_grad():
+        a = v(mel.to(dev), z.to(dev))
+        z2 = z.clone()
+        s = 150000
+        z2[0, 0, s:] += 1.0
+        b = v(mel.to(dev), z2.to(dev))
+    assert bool(torch.isfinite(a).all())
+    assert torch.equal(a[0, 0, :s], b[0, 0, :s]) and not torch.equal(a[0, 0, s:], b[0, 0, s:])
+    assert torch.equal(a[1], b[1])
+    # head of the utterance against the oracle (causal: a prefix is self-contained)
+    n = 3 * 256
+    ref = C.vocode_student(ssd, tsd, mel[:1, :, :8], z[:1, :, : 8 * 256])
+    assert float((a[0, 0, :n].cpu() - ref[0, 0, :n]).abs().max()) <= TOL
+
+
+# ------------------------------------------------ heads ------------------------------------------------
+def test_mulaw_bit_exact(dev):
+    import tts_cube_b200 as cube
+    d = load_golden("heads.npz")
+    m = cube.MULAWOutput()
+    for xs, qs in ((d["mulaw_x"], d["mulaw_q"]), (d["mulaw_nb_x"], d["mulaw_nb_q"])):
+        q = m.encode(torch.from_numpy(xs).to(dev))
+        assert q.dtype == torch.int64
+        assert np.array_equal(q.cpu().numpy(), qs)
+    assert np.array_equal(m.decode(torch.arange(256, device=dev)).cpu().numpy(), d["mulaw_table"])
+    assert m.encode(m.decode(torch.arange(256, device=dev))).cpu().tolist() == list(range(256))
+    # a large seeded sweep against the oracle restatement, plus shapes / empties
+    g = torch.Generator().manual_seed(123)
+    x = torch.rand(1 << 20, generator=g) * 2.2 - 1.1
+    assert torch.equal(m.encode(x.to(dev)).cpu(), W.mulaw_encode_by_edges(x, d["mulaw_edges"]))
+    assert m.encode(torch.zeros(3, 0, device=dev)).shape == (3, 0)
+    x3 = torch.rand(2, 5, 7, generator=g) * 2 - 1
+    assert torch.equal(m.encode(x3.to(dev)).cpu(), W.mulaw_encode(x3))
+
+
+def test_raw_mol_gaussian_categorical(dev):
+    import tts_cube_b200 as cube
+    d = load_golden("heads.npz")
+    r = cube.RAWOutput()
+    assert np.array_equal(r.encode(torch.from_numpy(d["raw_x"]).to(dev)).cpu().numpy(), d["raw_q"])
+    assert np.array_equal(r.decode(torch.arange(256, device=dev)).cpu().numpy(), d["raw_table"])
+    y, um, ux = (torch.from_numpy(d[k]) for k in ("mol_y", "mol_u_mix", "mol_u_x"))
+    xm = cube.MOLOutput().sample(y.to(dev), u_mix=um.to(dev), u_x=ux.to(dev)).cpu()
+    ok = W.mol_argmax_margin(y, um) > 1e-5          # float32 near-ties may legitimately flip the pick
+    assert float(ok.float().mean()) > 0.99
+    assert float((xm - torch.from_numpy(d["mol_x"]))[ok].abs().max()) <= 1e-5
+    xg = cube.GaussianOutput().sample(torch.from_numpy(d["gau_y"]).to(dev), eps=torch.from_numpy(d["gau_eps"]).to(dev)).cpu()
+    assert float((xg - torch.from_numpy(d["gau_x"])).abs().max()) <= 1e-6
+    g = torch.Generator().manual_seed(5)
+    logits = torch.randn(4, 33, 256, generator=g) * 3
+    u = torch.empty(4, 33, 256).uniform_(1e-5, 1 - 1e-5, generator=g)
+    from tts_cube_b200.heads import _categorical
+    idx = _categorical(logits.to(dev), u.to(dev)).cpu()
+    ref = W.categorical_sample_gumbel(logits, u)
+    ok = W.categorical_margin(logits, u) > 1e-4
+    assert torch.equal(idx[ok], ref[ok]) and float(ok.float().mean()) > 0.99
+    # sample() = decode(categorical): values come from the 256-entry table
+    s = cube.MULAWOutput().sample(logits.to(dev), u.to(dev)).cpu()
+    assert torch.equal(s[ok], W.mulaw_decode(ref)[ok])

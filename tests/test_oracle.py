@@ -1,0 +1,111 @@
+"""Pin the CPU oracles against outputs of the UNMODIFIED reference (tests/golden/*.npz, produced by
+oracle/make_goldens.py in the build container).  CPU only."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_cfg, golden_weights, load_golden
+from oracle import clarinet_ref as C, heads_ref as W, hifigan_ref as H
+
+
+@pytest.mark.parametrize("name", ["hifigan_mini.npz", "hifigan_mini_rb2.npz"])
+def test_hifigan_oracle_matches_reference_mini(name):
+    d = load_golden(name)
+    y = H.generator_forward(golden_weights(d), golden_cfg(d), torch.from_numpy(d["mel"]))
+    assert y.shape == d["wav"].shape
+    assert float(np.abs(y.numpy() - d["wav"]).max()) <= 1e-6
+    assert float(np.abs(d["wav"]).max()) > 0.3  # the fixture is loud: the check is not vacuous
+
+
+def test_hifigan_oracle_matches_reference_trained(neb):
+    sd, cfg = neb
+    d = load_golden("hifigan_neb.npz")
+    y = H.generator_forward(sd, cfg, torch.from_numpy(d["mel"]))
+    assert float(np.abs(y.numpy() - d["wav"]).max()) <= 1e-6
+    assert np.array_equal(H.wav_to_int16(y).squeeze(1).numpy(), d["wav_int16"])
+
+
+def test_hifigan_length_law():
+    # F=100 -> 24096 (neb rates); F=50 -> 12064 (config_v1)
+    assert H.out_len(H.CONFIG_NEB, 100) == 24096
+    assert H.out_len(H.CONFIG_V1, 50) == 12064
+    assert H.out_len(H.CONFIG_V1, 919) == 220624
+
+
+def test_hifigan_ragged_equals_alone():
+    d = load_golden("hifigan_mini.npz")
+    sd, cfg = golden_weights(d), golden_cfg(d)
+    mel = torch.from_numpy(d["mel"])
+    y = H.generator_forward_ragged(sd, cfg, mel, [13, 7])
+    alone = H.generator_forward(sd, cfg, mel[1:2, :, :7])
+    assert torch.equal(y[1, :, : alone.shape[2]], alone[0])
+    assert float(y[1, :, alone.shape[2]:].abs().max()) == 0.0
+
+
+def test_heads_oracle_matches_reference():
+    d = load_golden("heads.npz")
+    x = torch.from_numpy(d["mulaw_x"])
+    assert np.array_equal(W.mulaw_encode(x).numpy(), d["mulaw_q"])
+    assert np.array_equal(W.mulaw_decode_table().numpy(), d["mulaw_table"])
+    # the reference's embedded vector (cube/networks/loss.py:312) and SURVEY Appendix B answers
+    assert W.mulaw_encode(torch.tensor([1, 0.9, 0, -0.9, -1.0])).tolist() == [255, 253, 128, 2, 0]
+    assert np.array_equal(W.mulaw_encode(torch.from_numpy(d["mulaw_nb_x"])).numpy(), d["mulaw_nb_q"])
+    # the edge table reproduces encode bit for bit, including the 765 hardest inputs
+    edges = d["mulaw_edges"]
+    assert np.all(np.diff(edges) > 0)
+    assert np.array_equal(W.mulaw_encode_by_edges(x, edges).numpy(), d["mulaw_q"])
+    assert np.array_equal(W.mulaw_encode_by_edges(torch.from_numpy(d["mulaw_nb_x"]), edges).numpy(), d["mulaw_nb_q"])
+    # encode(decode(k)) == k for all 256 codes
+    assert W.mulaw_encode(W.mulaw_decode_table()).tolist() == list(range(256))
+    xr = torch.from_numpy(d["raw_x"])
+    assert np.array_equal(W.raw_encode(xr).numpy(), d["raw_q"])
+    assert np.array_equal(W.raw_decode(torch.arange(256)).numpy(), d["raw_table"])
+    xm = W.mol_sample(torch.from_numpy(d["mol_y"]), torch.from_numpy(d["mol_u_mix"]), torch.from_numpy(d["mol_u_x"]))
+    assert np.array_equal(xm.numpy(), d["mol_x"])
+    xg = W.gaussian_sample(torch.from_numpy(d["gau_y"]), torch.from_numpy(d["gau_eps"]))
+    assert np.array_equal(xg.numpy(), d["gau_x"])
+
+
+def test_upsamplers_match_reference():
+    d = load_golden("upsample2.npz")
+    tsd = golden_weights(d)
+    mel = torch.from_numpy(d["mel"])
+    c = C.upsample_mel(tsd, mel)
+    assert c.shape == d["c_up"].shape
+    assert float(np.abs(c.numpy() - d["c_up"]).max()) <= 1e-6
+    assert np.array_equal(W.upsample_repeat(mel[:, :4], 3).numpy(), d["rep3"])
+    assert float(np.abs(W.upsample_linear(mel[:, :4], 3).numpy() - d["lin3"]).max()) <= 1e-6
+
+
+def test_clarinet_checkpoints_strict_and_regression(clarinet_weights):
+    ssd, tsd, trained = clarinet_weights
+    C.check_state_dict(ssd, "student")
+    C.check_state_dict(tsd, "teacher")
+    assert C.student_blocks_of(ssd) == [6, 6, 6, 24] and C.teacher_blocks_of(tsd) == 24
+    if not trained:
+        pytest.skip("shipped checkpoints not staged: regression snapshot needs them")
+    d = load_golden("clarinet_regress.npz")
+    x = C.vocode_student(ssd, tsd, torch.from_numpy(d["mel"]), torch.from_numpy(d["z"]))
+    assert float(np.abs(x.numpy() - d["wav"]).max()) <= 1e-5
+
+
+def test_clarinet_self_consistency_probe(clarinet_weights):
+    """the forward code is not in the reference, so the restatement's free
+    choices are checked for self-consistency - student samples must be far likelier under the
+    teacher with dilation 3^(i mod 6) and sqrt(.5) residual scaling than without."""
+    ssd, tsd, trained = clarinet_weights
+    if not trained:
+        pytest.skip("needs the shipped checkpoints")
+    torch.manual_seed(0)
+    mel = C.synthetic_mel01(1, 14, seed=21)
+    c_up = C.upsample_mel(tsd, mel)
+    z = torch.randn(1, 1, c_up.shape[2], generator=torch.Generator().manual_seed(5))
+    nll = {}
+    for name, base, rs in (("3^n", 3, math.sqrt(0.5)), ("2^n", 2, math.sqrt(0.5)), ("3^n,noscale", 3, 1.0)):
+        x = C.student_forward(ssd, z, c_up, dil_base=base, res_scale=rs)
+        nll[name] = C.teacher_nll(tsd, x, c_up, dil_base=base, res_scale=rs)
+    assert nll["3^n"] < nll["2^n"] - 0.3, nll
+    assert nll["3^n"] < nll["3^n,noscale"] - 3.0, nll
+    assert nll["3^n"] < -1.0, nll

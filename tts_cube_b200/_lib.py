@@ -1,0 +1,93 @@
+"""ctypes binding of libcube_vocoder.so (C ABI: include/cube_vocoder.h).
+
+There is deliberately no fallback: if the shared library is missing or cannot be loaded, importing
+any compute entry point raises.  The library is built in-tree by ``__graft_entry__.build()`` /
+``python -m tts_cube_b200.build``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcube_vocoder.so")
+
+MAX_UPS, MAX_RBK, MAX_DIL, MAX_FLOWS = 8, 8, 8, 8
+ARCH_HIFIGAN, ARCH_PWN_STUDENT = 0, 1
+MATH_FP32_SIMT, MATH_TC_SPLIT16 = 0, 1
+
+
+class VocConfig(C.Structure):
+    _fields_ = [
+        ("arch", C.c_int32), ("math", C.c_int32), ("num_mels", C.c_int32),
+        ("upsample_initial_channel", C.c_int32), ("n_ups", C.c_int32),
+        ("upsample_rates", C.c_int32 * MAX_UPS), ("upsample_kernel_sizes", C.c_int32 * MAX_UPS),
+        ("resblock_type", C.c_int32), ("n_resblock_kernels", C.c_int32),
+        ("resblock_kernel_sizes", C.c_int32 * MAX_RBK), ("n_dilations", C.c_int32 * MAX_RBK),
+        ("resblock_dilations", (C.c_int32 * MAX_DIL) * MAX_RBK),
+        ("n_flows", C.c_int32), ("flow_blocks", C.c_int32 * MAX_FLOWS),
+        ("res_channels", C.c_int32), ("gate_channels", C.c_int32), ("skip_channels", C.c_int32),
+        ("kernel_size", C.c_int32), ("front_kernel", C.c_int32),
+        ("dilation_base", C.c_int32), ("dilation_cycle", C.c_int32),
+        ("n_upsample", C.c_int32), ("upsample_scales", C.c_int32 * 4),
+    ]
+
+
+class CubeVocError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/cube_vocoder.h declares
+_P = C.c_void_p
+SYMBOLS = {
+    "cube_voc_create": (C.c_int, [C.POINTER(_P), C.POINTER(VocConfig), C.c_int]),
+    "cube_voc_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
+    "cube_voc_finalize": (C.c_int, [_P]),
+    "cube_voc_out_len": (C.c_int64, [_P, C.c_int64]),
+    "cube_voc_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int64, _P]),
+    "cube_voc_forward_host": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int64]),
+    "cube_voc_get_cond": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P]),
+    "cube_voc_last_launches": (C.c_int64, [_P]),
+    "cube_voc_workspace_bytes": (C.c_int64, [_P]),
+    "cube_voc_set_profile": (C.c_int, [_P, C.c_int]),
+    "cube_voc_get_profile": (C.c_int, [_P, _P, _P, C.c_int]),
+    "cube_voc_destroy": (None, [_P]),
+    "cube_voc_last_error": (C.c_char_p, []),
+    "cube_voc_build_info": (C.c_char_p, []),
+    "cube_mulaw_encode": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "cube_mulaw_decode": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "cube_raw_encode": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "cube_raw_decode": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "cube_mol_sample": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_float, C.c_float, _P]),
+    "cube_gaussian_sample": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    "cube_categorical_sample": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P]),
+    "cube_wav_to_int16": (C.c_int, [_P, _P, C.c_int64, _P]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raise loudly if it is not there."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CubeVocError(
+                f"{LIB_PATH} not found - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  tts_cube_b200 has no CPU or PyTorch fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)  # AttributeError if the ABI and the header drifted apart
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise CubeVocError(lib().cube_voc_last_error().decode("utf-8", "replace"))
+
+
+def build_info() -> str:
+    return lib().cube_voc_build_info().decode()

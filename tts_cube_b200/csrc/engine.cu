@@ -1,0 +1,1018 @@
+// libcube_vocoder.so - engine + C ABI (include/cube_vocoder.h).
+//
+// The engine owns: the folded / repacked weights on the device, a grow-only device workspace, and
+// the launch plan of one forward pass.  Host code is plain C++; all compute is in the kernels of
+// conv_simt.cuh / heads.cuh / tc_conv.cuh.  There is no CPU compute path.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/cube_vocoder.h"
+#include "conv_simt.cuh"
+#include "heads.cuh"
+
+#define CUBE_VERSION "0.1.0"
+
+namespace cube {
+
+static thread_local char g_err[1024] = "";
+
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define CU_TRY(expr)                                                                       \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+
+struct DevBuf {
+  float* p = nullptr;
+  size_t bytes = 0;
+};
+
+// One dense layer in kernel form.
+struct PackedConv {
+  float* W = nullptr;      // device [nphase][Ktot][Mpad]
+  float* bias = nullptr;   // device [Mpad]
+  int M = 0, Mpad = 0, Ktot = 0, nphase = 1;
+};
+
+struct ProfRec { std::string name; cudaEvent_t a, b; };
+
+}  // namespace cube
+
+using namespace cube;
+
+struct cube_voc {
+  cube_voc_config cfg;
+  int device = 0;
+  bool finalized = false;
+  std::map<std::string, HostTensor> host_w;
+  std::vector<void*> dev_allocs;           // weights
+  // workspace (grow-only)
+  std::map<std::string, DevBuf> ws;
+  int* d_lens = nullptr; size_t lens_cap = 0;
+  std::vector<int> h_lens;                  // pageable on purpose: the runtime stages small
+                                            // pageable H2D copies before returning, so the vector
+                                            // can be rewritten by the next (still queued) forward
+  // staging for forward_host
+  void* hs_in = nullptr; size_t hs_in_cap = 0;
+  float* d_mel = nullptr; size_t d_mel_cap = 0;
+  float* d_noise = nullptr; size_t d_noise_cap = 0;
+  float* d_wav = nullptr; size_t d_wav_cap = 0;
+  int16_t* d_wav16 = nullptr; size_t d_wav16_cap = 0;
+  cudaStream_t own_stream = nullptr;
+  int64_t launches = 0;
+  int sm_count = 148;
+  // profiling
+  bool profile = false;
+  std::vector<ProfRec> prof;
+  // HiFi-GAN packed layers
+  PackedConv conv_pre, conv_post_w;
+  std::vector<PackedConv> ups;
+  std::vector<std::vector<PackedConv>> rb_c1, rb_c2;  // [resblock idx][dilation idx]
+  // ClariNet packed layers
+  struct Flow { PackedConv front, final1, final3; std::vector<PackedConv> gate, resskip; };
+  std::vector<Flow> flows;
+  struct Up2 { float w[192]; float bias; int s; };
+  std::vector<Up2> up2;
+  // last-forward geometry (for get_cond)
+  int last_B = 0; int64_t last_T = 0;
+};
+
+namespace cube {
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+static int dev_upload(cube_voc* h, const std::vector<float>& v, float** out) {
+  float* d = nullptr;
+  CU_TRY(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(float)));
+  CU_TRY(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->dev_allocs.push_back(d);
+  *out = d;
+  return 0;
+}
+
+static int ws_get(cube_voc* h, const char* name, size_t n_floats, float** out) {
+  DevBuf& b = h->ws[name];
+  const size_t need = n_floats * sizeof(float);
+  if (b.bytes < need) {
+    if (b.p) CU_TRY(cudaFree(b.p));
+    b.p = nullptr; b.bytes = 0;
+    CU_TRY(cudaMalloc(&b.p, need));
+    b.bytes = need;
+  }
+  *out = b.p;
+  return 0;
+}
+
+// weight-norm fold: w = g * v / ||v||_2 over every dim but 0  (torch.nn.utils.weight_norm, dim=0;
+// hifigan/models.py:118-125).  Norm accumulated in double, result rounded to float.
+static int get_weight(cube_voc* h, const std::string& base, HostTensor* out) {
+  auto it = h->host_w.find(base + ".weight");
+  if (it != h->host_w.end()) { *out = it->second; return 0; }
+  auto ig = h->host_w.find(base + ".weight_g"), iv = h->host_w.find(base + ".weight_v");
+  if (ig == h->host_w.end() || iv == h->host_w.end()) return fail("missing weight '%s.weight[_g/_v]'", base.c_str());
+  const HostTensor& g = ig->second; const HostTensor& v = iv->second;
+  const int64_t n0 = v.shape[0], inner = v.numel() / n0;
+  if (g.numel() != n0) return fail("weight_g of '%s' has %lld elements, expected %lld", base.c_str(), (long long)g.numel(), (long long)n0);
+  out->shape = v.shape;
+  out->data.resize(v.data.size());
+  for (int64_t i = 0; i < n0; ++i) {
+    double ss = 0;
+    for (int64_t j = 0; j < inner; ++j) { double x = v.data[i * inner + j]; ss += x * x; }
+    const float scale = (float)((double)g.data[i] / sqrt(ss));
+    for (int64_t j = 0; j < inner; ++j) out->data[i * inner + j] = v.data[i * inner + j] * scale;
+  }
+  return 0;
+}
+
+static int get_bias(cube_voc* h, const std::string& base, int64_t n, const HostTensor** out) {
+  auto it = h->host_w.find(base + ".bias");
+  if (it == h->host_w.end()) return fail("missing '%s.bias'", base.c_str());
+  if (it->second.numel() != n) return fail("'%s.bias' has %lld elements, expected %lld", base.c_str(), (long long)it->second.numel(), (long long)n);
+  *out = &it->second;
+  return 0;
+}
+
+static int expect_shape(const std::string& name, const HostTensor& t, std::initializer_list<int64_t> s) {
+  std::vector<int64_t> e(s);
+  if (t.shape != e) {
+    std::string got, exp;
+    for (auto x : t.shape) got += std::to_string(x) + ",";
+    for (auto x : e) exp += std::to_string(x) + ",";
+    return fail("weight '%s' has shape [%s], expected [%s]", name.c_str(), got.c_str(), exp.c_str());
+  }
+  return 0;
+}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Conv1d weight [M][C][K] -> packed [C*K][Mpad]
+static int pack_conv1d(cube_voc* h, const std::string& base, int M, int C, int K, PackedConv* pc) {
+  HostTensor w; const HostTensor* b;
+  if (get_weight(h, base, &w)) return 1;
+  if (expect_shape(base, w, {M, C, K})) return 1;
+  if (get_bias(h, base, M, &b)) return 1;
+  pc->M = M; pc->Mpad = round_up(M, 128); pc->Ktot = C * K; pc->nphase = 1;
+  std::vector<float> P((size_t)pc->Ktot * pc->Mpad, 0.f), B(pc->Mpad, 0.f);
+  for (int m = 0; m < M; ++m) {
+    B[m] = b->data[m];
+    for (int c = 0; c < C; ++c)
+      for (int k = 0; k < K; ++k) P[(size_t)(c * K + k) * pc->Mpad + m] = w.data[((size_t)m * C + c) * K + k];
+  }
+  if (dev_upload(h, P, &pc->W)) return 1;
+  return dev_upload(h, B, &pc->bias);
+}
+
+// ConvTranspose1d weight [C][M][K], stride u -> per output phase r a (J-tap, dilation 1) correlation:
+//   out[t = q*u + r - p] = sum_c sum_jj Wr[c*J + jj][m] * x[c][q - (J-1) + jj],  k = r + (J-1-jj)*u
+static int pack_convT(cube_voc* h, const std::string& base, int C, int M, int K, int u, PackedConv* pc, int* J_out) {
+  HostTensor w; const HostTensor* b;
+  if (get_weight(h, base, &w)) return 1;
+  if (expect_shape(base, w, {C, M, K})) return 1;
+  if (get_bias(h, base, M, &b)) return 1;
+  const int J = (K + u - 1) / u;
+  pc->M = M; pc->Mpad = round_up(M, 128); pc->Ktot = C * J; pc->nphase = u;
+  std::vector<float> P((size_t)u * pc->Ktot * pc->Mpad, 0.f), B(pc->Mpad, 0.f);
+  for (int m = 0; m < M; ++m) B[m] = b->data[m];
+  for (int r = 0; r < u; ++r)
+    for (int c = 0; c < C; ++c)
+      for (int jj = 0; jj < J; ++jj) {
+        const int k = r + (J - 1 - jj) * u;
+        if (k >= K) continue;
+        for (int m = 0; m < M; ++m)
+          P[((size_t)r * pc->Ktot + (size_t)c * J + jj) * pc->Mpad + m] = w.data[((size_t)c * M + m) * K + k];
+      }
+  *J_out = J;
+  if (dev_upload(h, P, &pc->W)) return 1;
+  return dev_upload(h, B, &pc->bias);
+}
+
+// Small conv (M <= 2): [M][C][K] -> [C*K][M]
+static int pack_small(cube_voc* h, const std::string& base, int M, int C, int K, PackedConv* pc) {
+  HostTensor w; const HostTensor* b;
+  if (get_weight(h, base, &w)) return 1;
+  if (expect_shape(base, w, {M, C, K})) return 1;
+  if (get_bias(h, base, M, &b)) return 1;
+  pc->M = M; pc->Mpad = M; pc->Ktot = C * K;
+  std::vector<float> P((size_t)C * K * M), B(M);
+  for (int m = 0; m < M; ++m) {
+    B[m] = b->data[m];
+    for (int c = 0; c < C; ++c)
+      for (int k = 0; k < K; ++k) P[(size_t)(c * K + k) * M + m] = w.data[((size_t)m * C + c) * K + k];
+  }
+  if (dev_upload(h, P, &pc->W)) return 1;
+  return dev_upload(h, B, &pc->bias);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+struct Launcher {
+  cube_voc* h;
+  cudaStream_t st;
+  int err = 0;
+  const char* cur = "";
+
+  void begin(const char* name) {
+    cur = name;
+    if (h->profile) {
+      ProfRec r; r.name = name;
+      cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+      cudaEventRecord(r.a, st);
+      h->prof.push_back(r);
+    }
+  }
+  void end() {
+    if (h->profile) cudaEventRecord(h->prof.back().b, st);
+  }
+
+  static int pick_chunk(const Seg& s, int BM, int BN, size_t budget) {
+    const int span = (s.taps - 1) * s.dil;
+    const int XW = span <= BN ? BN + span : s.taps * BN;
+    const size_t per = (size_t)(((XW + 3) & ~3) + s.taps * BM) * sizeof(float);
+    int c = (int)(budget / per);
+    if (c < 1) c = 1;
+    if (c > s.C) c = s.C;
+    if (c > 32) c = 32;
+    return c;
+  }
+  static size_t smem_of(const Seg& s, int BM, int BN) {
+    const int span = (s.taps - 1) * s.dil;
+    const int XW = span <= BN ? BN + span : s.taps * BN;
+    return (size_t)s.ci_chunk * (((XW + 3) & ~3) + s.taps * BM) * sizeof(float);
+  }
+
+  template <int TM, int WM, int TN, int WN>
+  void launch_tile(ConvP& p, int B) {
+    constexpr int BM = TM * WM, BN = 32 * TN * WN;
+    size_t smem = 0;
+    for (int s = 0; s < p.nseg; ++s) {
+      p.seg[s].ci_chunk = pick_chunk(p.seg[s], BM, BN, 56 * 1024);
+      smem = std::max(smem, smem_of(p.seg[s], BM, BN));
+    }
+    static bool attr_set[64] = {false};
+    const int dv = h->device & 63;
+    if (!attr_set[dv]) {
+      cudaFuncSetAttribute(conv_tile_kernel<TM, WM, TN, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      attr_set[dv] = true;
+    }
+    dim3 grid((p.Q + BN - 1) / BN, (p.M + BM - 1) / BM, B * p.nphase);
+    conv_tile_kernel<TM, WM, TN, WN><<<grid, 256, smem, st>>>(p);
+    check();
+  }
+
+  // choose the tile by output-channel count
+  void conv(ConvP& p, int B) {
+    if (err) return;
+    if (p.M <= 32) launch_tile<8, 4, 8, 2>(p, B);       // 32 x 512
+    else launch_tile<8, 8, 8, 1>(p, B);                  // 64 x 256
+  }
+
+  void small(SmallP& p, int B, int MO) {
+    if (err) return;
+    constexpr int TPT = 4, BN = 256 * TPT;
+    const int span = (p.taps - 1) * p.dil;
+    const int XP = (BN + span) | 1;
+    int cic = (int)((60 * 1024 - (size_t)(p.C * p.taps * MO + 4) * 4) / ((size_t)XP * 4));
+    if (cic > p.C) cic = p.C;
+    if (cic < 1) cic = 1;
+    p.ci_chunk = cic;
+    const size_t smem = ((size_t)((p.C * p.taps * MO + 3) & ~3) + (size_t)cic * XP) * sizeof(float);
+    dim3 grid((p.L_out + BN - 1) / BN, B);
+    static bool a1[64] = {false}, a2[64] = {false};
+    const int dv = h->device & 63;
+    if (MO == 1) {
+      if (!a1[dv]) { cudaFuncSetAttribute(conv_small_kernel<1, TPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); a1[dv] = true; }
+      conv_small_kernel<1, TPT><<<grid, 256, smem, st>>>(p);
+    } else {
+      if (!a2[dv]) { cudaFuncSetAttribute(conv_small_kernel<2, TPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); a2[dv] = true; }
+      conv_small_kernel<2, TPT><<<grid, 256, smem, st>>>(p);
+    }
+    check();
+  }
+
+  void check() {
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess && !err) err = fail("kernel launch failed in '%s': %s", cur, cudaGetErrorString(e));
+  }
+};
+
+static Seg make_seg(const float* src, long long bstride, int C, int L, int taps, int dil, int off0,
+                    int preact, float slope, const int* lens = nullptr) {
+  Seg s;
+  memset(&s, 0, sizeof(s));
+  s.src = src; s.bstride = bstride; s.C = C; s.L = L; s.taps = taps; s.dil = dil; s.off0 = off0;
+  s.preact = preact; s.slope = slope; s.lens = lens; s.ci_chunk = 1;
+  return s;
+}
+
+static ConvP make_conv(const PackedConv& pc) {
+  ConvP p;
+  memset(&p, 0, sizeof(p));
+  p.W = pc.W; p.bias = pc.bias; p.M = pc.M; p.Mpad = pc.Mpad; p.nphase = 1; p.ostride = 1;
+  p.w_phase_stride = (long long)pc.Ktot * pc.Mpad;
+  p.epi = EPI_LINEAR; p.post = POST_NONE; p.acc_mode = ACC_NONE; p.acc_div = 1.f; p.scale = 1.f;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: strict weight check, fold, repack, upload
+// ------------------------------------------------------------------------------------------------
+static int finalize_hifigan(cube_voc* h) {
+  const cube_voc_config& c = h->cfg;
+  const int C0 = c.upsample_initial_channel;
+  if (pack_conv1d(h, "conv_pre", C0, c.num_mels, 7, &h->conv_pre)) return 1;
+  int ch = C0;
+  h->ups.resize(c.n_ups);
+  const int nk = c.n_resblock_kernels;
+  h->rb_c1.assign(c.n_ups * nk, {});
+  h->rb_c2.assign(c.n_ups * nk, {});
+  for (int i = 0; i < c.n_ups; ++i) {
+    int J;
+    if (pack_convT(h, "ups." + std::to_string(i), ch, ch / 2, c.upsample_kernel_sizes[i], c.upsample_rates[i], &h->ups[i], &J)) return 1;
+    ch /= 2;
+    for (int j = 0; j < nk; ++j) {
+      const int idx = i * nk + j, k = c.resblock_kernel_sizes[j], nd = c.n_dilations[j];
+      h->rb_c1[idx].resize(nd);
+      h->rb_c2[idx].resize(c.resblock_type == 1 ? nd : 0);
+      for (int m = 0; m < nd; ++m) {
+        const std::string rb = "resblocks." + std::to_string(idx);
+        if (c.resblock_type == 1) {
+          if (pack_conv1d(h, rb + ".convs1." + std::to_string(m), ch, ch, k, &h->rb_c1[idx][m])) return 1;
+          if (pack_conv1d(h, rb + ".convs2." + std::to_string(m), ch, ch, k, &h->rb_c2[idx][m])) return 1;
+        } else {
+          if (pack_conv1d(h, rb + ".convs." + std::to_string(m), ch, ch, k, &h->rb_c1[idx][m])) return 1;
+        }
+      }
+    }
+  }
+  return pack_small(h, "conv_post", 1, ch, 7, &h->conv_post_w);
+}
+
+static int finalize_student(cube_voc* h) {
+  const cube_voc_config& c = h->cfg;
+  const int R = c.res_channels, G = c.gate_channels, S = c.skip_channels, CI = c.num_mels, K = c.kernel_size;
+  if (R != S) return fail("res_channels must equal skip_channels (got %d, %d)", R, S);
+  h->flows.resize(c.n_flows);
+  for (int f = 0; f < c.n_flows; ++f) {
+    cube_voc::Flow& fl = h->flows[f];
+    const std::string fp = "iafs." + std::to_string(f) + ".";
+    if (pack_conv1d(h, fp + "front_conv.0.conv", R, 1, c.front_kernel, &fl.front)) return 1;
+    const int nb = c.flow_blocks[f];
+    fl.gate.resize(nb); fl.resskip.resize(nb);
+    for (int i = 0; i < nb; ++i) {
+      const std::string bp = fp + "res_blocks." + std::to_string(i) + ".";
+      HostTensor wf, wg, wfc, wgc, wr, ws;
+      const HostTensor *bf, *bg, *bfc, *bgc, *br, *bs;
+      if (get_weight(h, bp + "filter_conv.conv", &wf) || expect_shape(bp + "filter_conv.conv", wf, {G, R, K})) return 1;
+      if (get_weight(h, bp + "gate_conv.conv", &wg) || expect_shape(bp + "gate_conv.conv", wg, {G, R, K})) return 1;
+      if (get_weight(h, bp + "filter_conv_c", &wfc) || expect_shape(bp + "filter_conv_c", wfc, {G, CI, 1})) return 1;
+      if (get_weight(h, bp + "gate_conv_c", &wgc) || expect_shape(bp + "gate_conv_c", wgc, {G, CI, 1})) return 1;
+      if (get_weight(h, bp + "res_conv", &wr) || expect_shape(bp + "res_conv", wr, {R, G, 1})) return 1;
+      if (get_weight(h, bp + "skip_conv", &ws) || expect_shape(bp + "skip_conv", ws, {S, G, 1})) return 1;
+      if (get_bias(h, bp + "filter_conv.conv", G, &bf) || get_bias(h, bp + "gate_conv.conv", G, &bg) ||
+          get_bias(h, bp + "filter_conv_c", G, &bfc) || get_bias(h, bp + "gate_conv_c", G, &bgc) ||
+          get_bias(h, bp + "res_conv", R, &br) || get_bias(h, bp + "skip_conv", S, &bs)) return 1;
+      // gate GEMM: rows interleaved (2j = filter j, 2j+1 = gate j); K = [h: c*K + k][cond: c]
+      PackedConv& pg = fl.gate[i];
+      pg.M = 2 * G; pg.Mpad = round_up(2 * G, 128); pg.Ktot = R * K + CI; pg.nphase = 1;
+      std::vector<float> P((size_t)pg.Ktot * pg.Mpad, 0.f), Bv(pg.Mpad, 0.f);
+      for (int j = 0; j < G; ++j) {
+        Bv[2 * j] = bf->data[j] + bfc->data[j];
+        Bv[2 * j + 1] = bg->data[j] + bgc->data[j];
+        for (int cc = 0; cc < R; ++cc)
+          for (int k = 0; k < K; ++k) {
+            P[(size_t)(cc * K + k) * pg.Mpad + 2 * j] = wf.data[((size_t)j * R + cc) * K + k];
+            P[(size_t)(cc * K + k) * pg.Mpad + 2 * j + 1] = wg.data[((size_t)j * R + cc) * K + k];
+          }
+        for (int cc = 0; cc < CI; ++cc) {
+          P[(size_t)(R * K + cc) * pg.Mpad + 2 * j] = wfc.data[(size_t)j * CI + cc];
+          P[(size_t)(R * K + cc) * pg.Mpad + 2 * j + 1] = wgc.data[(size_t)j * CI + cc];
+        }
+      }
+      if (dev_upload(h, P, &pg.W) || dev_upload(h, Bv, &pg.bias)) return 1;
+      // res/skip GEMM: rows [0,R) res_conv, [R,R+S) skip_conv; K = G
+      PackedConv& pr = fl.resskip[i];
+      pr.M = R + S; pr.Mpad = round_up(R + S, 128); pr.Ktot = G; pr.nphase = 1;
+      std::vector<float> P2((size_t)G * pr.Mpad, 0.f), B2(pr.Mpad, 0.f);
+      for (int m = 0; m < R; ++m) {
+        B2[m] = br->data[m];
+        for (int cc = 0; cc < G; ++cc) P2[(size_t)cc * pr.Mpad + m] = wr.data[(size_t)m * G + cc];
+      }
+      for (int m = 0; m < S; ++m) {
+        B2[R + m] = bs->data[m];
+        for (int cc = 0; cc < G; ++cc) P2[(size_t)cc * pr.Mpad + R + m] = ws.data[(size_t)m * G + cc];
+      }
+      if (dev_upload(h, P2, &pr.W) || dev_upload(h, B2, &pr.bias)) return 1;
+    }
+    if (pack_conv1d(h, fp + "final_conv.1.conv", S, S, 1, &fl.final1)) return 1;
+    if (pack_small(h, fp + "final_conv.3.conv", 2, S, 1, &fl.final3)) return 1;
+  }
+  // UpsampleNet2 (teacher's upsample_conv.{0,2}): [1,1,3,2s]
+  h->up2.resize(c.n_upsample);
+  for (int n = 0; n < c.n_upsample; ++n) {
+    const int s = c.upsample_scales[n];
+    if (s > 32) return fail("upsample scale %d > 32 unsupported", s);
+    const std::string base = "upsample_conv." + std::to_string(2 * n);
+    HostTensor w; const HostTensor* b;
+    if (get_weight(h, base, &w) || expect_shape(base, w, {1, 1, 3, 2 * s})) return 1;
+    if (get_bias(h, base, 1, &b)) return 1;
+    memset(h->up2[n].w, 0, sizeof(h->up2[n].w));
+    for (int i = 0; i < 3 * 2 * s; ++i) h->up2[n].w[i] = w.data[i];
+    h->up2[n].bias = b->data[0];
+    h->up2[n].s = s;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: HiFi-GAN
+// ------------------------------------------------------------------------------------------------
+static int64_t hifigan_len(const cube_voc_config& c, int64_t L, int upto) {
+  for (int i = 0; i < upto; ++i) {
+    const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
+    L = (L - 1) * u - 2 * ((k - u) / 2) + k;
+  }
+  return L;
+}
+
+static int upload_lens(cube_voc* h, const int32_t* n_frames, int B, int64_t Fmax, int nlevels, cudaStream_t st) {
+  const size_t need = (size_t)nlevels * B;
+  if (h->lens_cap < need) {
+    if (h->d_lens) CU_TRY(cudaFree(h->d_lens));
+    CU_TRY(cudaMalloc(&h->d_lens, need * sizeof(int)));
+    h->lens_cap = need;
+  }
+  h->h_lens.resize(need);
+  for (int b = 0; b < B; ++b) {
+    int64_t f = n_frames ? n_frames[b] : Fmax;
+    if (f < 0 || f > Fmax) return fail("n_frames[%d]=%lld outside [0, %lld]", b, (long long)f, (long long)Fmax);
+    for (int l = 0; l < nlevels; ++l) {
+      int64_t L;
+      if (h->cfg.arch == CUBE_VOC_HIFIGAN) L = f > 0 ? hifigan_len(h->cfg, f, l) : 0;
+      else { L = f; for (int i = 0; i < l; ++i) L *= h->cfg.upsample_scales[i]; }
+      h->h_lens[(size_t)l * B + b] = (int)L;
+    }
+  }
+  CU_TRY(cudaMemcpyAsync(h->d_lens, h->h_lens.data(), need * sizeof(int), cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+static int forward_hifigan(cube_voc* h, const float* mel, const int32_t* n_frames, float* wav, int16_t* wav16,
+                           int B, int64_t Fmax, cudaStream_t st) {
+  const cube_voc_config& c = h->cfg;
+  const int nU = c.n_ups, nk = c.n_resblock_kernels;
+  std::vector<int64_t> L(nU + 1);
+  for (int i = 0; i <= nU; ++i) L[i] = hifigan_len(c, Fmax, i);
+  if (L[nU] > 0x7fffffffLL / 2) return fail("utterance too long");
+  if (upload_lens(h, n_frames, B, Fmax, nU + 1, st)) return 1;
+  const int C0 = c.upsample_initial_channel;
+  size_t stage_max = (size_t)C0 * L[0];
+  for (int i = 0; i < nU; ++i) stage_max = std::max(stage_max, (size_t)(C0 >> (i + 1)) * L[i + 1]);
+  float *bufA, *bufB, *bufC, *bufD;
+  if (ws_get(h, "hA", stage_max * B, &bufA) || ws_get(h, "hB", stage_max * B, &bufB) ||
+      ws_get(h, "hC", stage_max * B, &bufC) || ws_get(h, "hD", stage_max * B, &bufD)) return 1;
+  Launcher lx{h, st};
+  const float LR = 0.1f;  // hifigan/models.py:8
+
+  // conv_pre: mel [B,80,F] -> D [B,C0,F]   (hifigan/models.py:101)
+  {
+    lx.begin("conv_pre");
+    ConvP p = make_conv(h->conv_pre);
+    p.nseg = 1;
+    p.seg[0] = make_seg(mel, (long long)c.num_mels * Fmax, c.num_mels, (int)Fmax, 7, 1, -3, PRE_NONE, 0.f, h->d_lens);
+    p.Q = (int)L[0]; p.L_out = (int)L[0]; p.out_lens = h->d_lens;
+    p.out = bufD; p.out_bstride = (long long)C0 * L[0];
+    lx.conv(p, B);
+    lx.end();
+  }
+  int ch = C0;
+  float* stage_in = bufD;
+  for (int i = 0; i < nU; ++i) {
+    const int u = c.upsample_rates[i], K = c.upsample_kernel_sizes[i], pad = (K - u) / 2;
+    const int J = (K + u - 1) / u;
+    const int Lin = (int)L[i], Lo = (int)L[i + 1];
+    const int cho = ch / 2;
+    const int* lens_in = h->d_lens + (size_t)i * B;
+    const int* lens_out = h->d_lens + (size_t)(i + 1) * B;
+    float *xu = bufA, *xt = bufB, *xr = bufC, *xs = bufD;
+    {  // x = ups[i](leaky_relu(x, 0.1))   (hifigan/models.py:103-104)
+      lx.begin("ups");
+      ConvP p = make_conv(h->ups[i]);
+      p.nseg = 1;
+      p.seg[0] = make_seg(stage_in, (long long)ch * Lin, ch, Lin, J, 1, -(J - 1), PRE_LRELU, LR, lens_in);
+      p.nphase = u; p.ostride = u;
+      for (int r = 0; r < u; ++r) p.ooff[r] = r - pad;
+      p.Q = (Lo - 1 + pad) / u + 1;
+      p.L_out = Lo; p.out_lens = lens_out;
+      p.out = xu; p.out_bstride = (long long)cho * Lo;
+      lx.conv(p, B);
+      lx.end();
+    }
+    ch = cho;
+    const long long bs = (long long)ch * Lo;
+    for (int j = 0; j < nk; ++j) {
+      const int idx = i * nk + j, k = c.resblock_kernel_sizes[j], nd = c.n_dilations[j];
+      const int accm = (j == 0) ? ACC_SET : (j == nk - 1 ? ACC_ADD_DIV : ACC_ADD);
+      const float* xcur = xu;
+      if (c.resblock_type == 1) {
+        for (int m = 0; m < nd; ++m) {  // hifigan/models.py:35-42
+          const int d = c.resblock_dilations[j][m];
+          lx.begin("rb_conv1");
+          ConvP p1 = make_conv(h->rb_c1[idx][m]);
+          p1.nseg = 1;
+          p1.seg[0] = make_seg(xcur, bs, ch, Lo, k, d, -((k * d - d) / 2), PRE_LRELU, LR);
+          p1.Q = Lo; p1.L_out = Lo; p1.out_lens = lens_out; p1.out = xt; p1.out_bstride = bs;
+          lx.conv(p1, B);
+          lx.end();
+          lx.begin("rb_conv2");
+          ConvP p2 = make_conv(h->rb_c2[idx][m]);
+          p2.nseg = 1;
+          p2.seg[0] = make_seg(xt, bs, ch, Lo, k, 1, -((k - 1) / 2), PRE_LRELU, LR);
+          p2.Q = Lo; p2.L_out = Lo; p2.out_lens = lens_out;
+          p2.epi = EPI_RESADD; p2.res = xcur; p2.res_bstride = bs;
+          const bool last = (m == nd - 1);
+          p2.out = last ? nullptr : xr; p2.out_bstride = bs;
+          if (last) { p2.acc = xs; p2.acc_bstride = bs; p2.acc_mode = accm; p2.acc_div = (float)nk; }
+          if (last && nk == 1) { p2.acc_mode = ACC_SET; }
+          lx.conv(p2, B);
+          lx.end();
+          xcur = xr;
+        }
+      } else {  // ResBlock2: x = conv(lrelu(x)) + x   (hifigan/models.py:63-68); ping-pong xt/xr
+        float* pp[2] = {xt, xr};
+        for (int m = 0; m < nd; ++m) {
+          const int d = c.resblock_dilations[j][m];
+          lx.begin("rb2_conv");
+          ConvP p1 = make_conv(h->rb_c1[idx][m]);
+          p1.nseg = 1;
+          p1.seg[0] = make_seg(xcur, bs, ch, Lo, k, d, -((k * d - d) / 2), PRE_LRELU, LR);
+          p1.Q = Lo; p1.L_out = Lo; p1.out_lens = lens_out;
+          p1.epi = EPI_RESADD; p1.res = xcur; p1.res_bstride = bs;
+          const bool last = (m == nd - 1);
+          p1.out = last ? nullptr : pp[m & 1]; p1.out_bstride = bs;
+          if (last) { p1.acc = xs; p1.acc_bstride = bs; p1.acc_mode = (nk == 1) ? ACC_SET : accm; p1.acc_div = (float)nk; }
+          lx.conv(p1, B);
+          lx.end();
+          xcur = pp[m & 1];
+        }
+      }
+    }
+    stage_in = xs;
+  }
+  {  // x = tanh(conv_post(leaky_relu(x)))  - default slope 0.01   (hifigan/models.py:112-114)
+    lx.begin("conv_post");
+    const int Lo = (int)L[nU];
+    SmallP p;
+    memset(&p, 0, sizeof(p));
+    p.src = stage_in; p.bstride = (long long)ch * Lo; p.C = ch; p.L = Lo;
+    p.taps = 7; p.dil = 1; p.off0 = -3; p.preact = PRE_LRELU; p.slope = 0.01f;
+    p.W = h->conv_post_w.W; p.bias = h->conv_post_w.bias;
+    p.out_lens = h->d_lens + (size_t)nU * B; p.L_out = Lo;
+    p.out = wav; p.out_bstride = Lo; p.out_i16 = wav16; p.epi = SEPI_TANH;
+    lx.small(p, B, 1);
+    lx.end();
+  }
+  return lx.err;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: ClariNet IAF student
+// ------------------------------------------------------------------------------------------------
+static int dilation_of(const cube_voc_config& c, int i) {
+  int d = 1;
+  for (int k = 0; k < i % c.dilation_cycle; ++k) d *= c.dilation_base;
+  return d;
+}
+
+static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frames, const float* noise,
+                           float* wav, int16_t* wav16, int B, int64_t Fmax, cudaStream_t st) {
+  const cube_voc_config& c = h->cfg;
+  if (!noise) return fail("the IAF student needs `noise` (z ~ N(0,1), [B,1,T])");
+  int64_t T64 = Fmax;
+  for (int n = 0; n < c.n_upsample; ++n) T64 *= c.upsample_scales[n];
+  if (T64 > 0x7fffffffLL / 2) return fail("utterance too long");
+  const int T = (int)T64;
+  const int R = c.res_channels, G = c.gate_channels, S = c.skip_channels, CI = c.num_mels, K = c.kernel_size;
+  if (upload_lens(h, n_frames, B, Fmax, c.n_upsample + 1, st)) return 1;
+  const int* lens_T = h->d_lens + (size_t)c.n_upsample * B;
+  float *cmid, *cup, *hb, *ob, *sk, *y1, *za, *zb;
+  if (ws_get(h, "c_up", (size_t)B * CI * T, &cup) || ws_get(h, "c_mid", (size_t)B * CI * (T / c.upsample_scales[c.n_upsample - 1] + 1), &cmid) ||
+      ws_get(h, "h", (size_t)B * R * T, &hb) || ws_get(h, "o", (size_t)B * G * T, &ob) ||
+      ws_get(h, "skip", (size_t)B * S * T, &sk) || ws_get(h, "y1", (size_t)B * S * T, &y1) ||
+      ws_get(h, "za", (size_t)B * T, &za) || ws_get(h, "zb", (size_t)B * T, &zb)) return 1;
+  Launcher lx{h, st};
+  // ---- conditioning: UpsampleNet2 (cube/networks/modules.py:357-375) ----
+  {
+    const float* src = mel;
+    int Lin = (int)Fmax, scale = 1;
+    for (int n = 0; n < c.n_upsample; ++n) {
+      lx.begin("upsample2d");
+      Up2dP p;
+      memset(&p, 0, sizeof(p));
+      const int s = h->up2[n].s;
+      p.src = src; p.out = (n == c.n_upsample - 1) ? cup : cmid;
+      p.src_lens = h->d_lens; p.lens_scale = scale;
+      p.nf = CI; p.L_in = Lin; p.L_out = Lin * s; p.s = s; p.pad = s / 2;
+      memcpy(p.w, h->up2[n].w, sizeof(p.w));
+      p.bias = h->up2[n].bias; p.slope = 0.4f;
+      dim3 grid((p.L_out + 255) / 256, CI, B);
+      upsample2d_kernel<<<grid, 256, 0, st>>>(p);
+      lx.check();
+      lx.end();
+      src = p.out; Lin = p.L_out; scale *= s;
+    }
+    if (c.n_upsample == 0) return fail("n_upsample must be >= 1");
+  }
+  h->last_B = B; h->last_T = T;
+  const float* zin = noise;
+  const float rs = sqrtf(0.5f);
+  for (int f = 0; f < c.n_flows; ++f) {
+    cube_voc::Flow& fl = h->flows[f];
+    const bool last_flow = (f == c.n_flows - 1);
+    float* zout = last_flow ? wav : ((f & 1) ? zb : za);
+    {  // h = relu(front_conv(z)) : causal k=32
+      lx.begin("front");
+      ConvP p = make_conv(fl.front);
+      p.nseg = 1;
+      p.seg[0] = make_seg(zin, T, 1, T, c.front_kernel, 1, -(c.front_kernel - 1), PRE_NONE, 0.f, lens_T);
+      p.Q = T; p.L_out = T; p.out_lens = lens_T; p.post = POST_RELU;
+      p.out = hb; p.out_bstride = (long long)R * T;
+      lx.conv(p, B);
+      lx.end();
+    }
+    const int nb = c.flow_blocks[f];
+    for (int i = 0; i < nb; ++i) {
+      const int d = dilation_of(c, i);
+      {  // o = tanh(filter(h) + filter_c(c)) * sigmoid(gate(h) + gate_c(c))
+        lx.begin("gate");
+        ConvP p = make_conv(fl.gate[i]);
+        p.nseg = 2;
+        p.seg[0] = make_seg(hb, (long long)R * T, R, T, K, d, -(K - 1) * d, PRE_NONE, 0.f);
+        p.seg[1] = make_seg(cup, (long long)CI * T, CI, T, 1, 1, 0, PRE_NONE, 0.f);
+        p.Q = T; p.L_out = T; p.out_lens = lens_T; p.epi = EPI_GATE;
+        p.out = ob; p.out_bstride = (long long)G * T;
+        lx.conv(p, B);
+        lx.end();
+      }
+      {  // h = (h + res(o)) * sqrt(.5);  skip += skip_conv(o)
+        lx.begin("resskip");
+        ConvP p = make_conv(fl.resskip[i]);
+        p.nseg = 1;
+        p.seg[0] = make_seg(ob, (long long)G * T, G, T, 1, 1, 0, PRE_NONE, 0.f);
+        p.Q = T; p.L_out = T; p.out_lens = lens_T; p.epi = EPI_RESSKIP;
+        p.Mh = R; p.scale = rs;
+        p.res = hb; p.res_bstride = (long long)R * T; p.out = hb; p.out_bstride = (long long)R * T;
+        p.skip = sk; p.skip_bstride = (long long)S * T; p.skip_set = (i == 0);
+        lx.conv(p, B);
+        lx.end();
+      }
+    }
+    {  // y1 = conv1x1(relu(skip))
+      lx.begin("final1");
+      ConvP p = make_conv(fl.final1);
+      p.nseg = 1;
+      p.seg[0] = make_seg(sk, (long long)S * T, S, T, 1, 1, 0, PRE_RELU, 0.f);
+      p.Q = T; p.L_out = T; p.out_lens = lens_T;
+      p.out = y1; p.out_bstride = (long long)S * T;
+      lx.conv(p, B);
+      lx.end();
+    }
+    {  // (mu, logs) = conv1x1(relu(y1));  z'[t+1] = z[t+1]*exp(logs[t]) + mu[t], z'[0] = 0
+      lx.begin("final3_iaf");
+      SmallP p;
+      memset(&p, 0, sizeof(p));
+      p.src = y1; p.bstride = (long long)S * T; p.C = S; p.L = T;
+      p.taps = 1; p.dil = 1; p.off0 = 0; p.preact = PRE_RELU;
+      p.W = fl.final3.W; p.bias = fl.final3.bias;
+      p.out_lens = lens_T; p.L_out = T; p.out = zout; p.out_bstride = T;
+      p.z = zin; p.z_bstride = T; p.epi = SEPI_IAF;
+      lx.small(p, B, 2);
+      lx.end();
+    }
+    zin = zout;
+  }
+  if (wav16 && !lx.err) {
+    lx.begin("to_int16");
+    const long long n = (long long)B * T;
+    wav_to_int16_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, st>>>(wav, wav16, n);
+    lx.check();
+    lx.end();
+  }
+  return lx.err;
+}
+
+static int ensure_device(cube_voc* h) {
+  CU_TRY(cudaSetDevice(h->device));
+  return 0;
+}
+
+template <typename T>
+static int grow(T** p, size_t* cap, size_t need_bytes) {
+  if (*cap >= need_bytes) return 0;
+  if (*p) CU_TRY(cudaFree(*p));
+  *p = nullptr; *cap = 0;
+  CU_TRY(cudaMalloc((void**)p, need_bytes));
+  *cap = need_bytes;
+  return 0;
+}
+
+static int head_grid(int64_t n) {
+  int64_t g = (n + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+static int tables_ready() {
+  static int dev_done[64] = {0};
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  if (dev < 64 && dev_done[dev]) return 0;
+  CU_TRY(upload_mulaw_tables());
+  if (dev < 64) dev_done[dev] = 1;
+  return 0;
+}
+
+}  // namespace cube
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* cube_voc_last_error(void) { return cube::g_err; }
+
+#define CUBE_STR2(x) #x
+#define CUBE_STR(x) CUBE_STR2(x)
+const char* cube_voc_build_info(void) {
+  return "libcube_vocoder " CUBE_VERSION " sm_100a (nvcc " CUBE_STR(__CUDACC_VER_MAJOR__) "." CUBE_STR(__CUDACC_VER_MINOR__) ")";
+}
+
+int cube_voc_create(cube_voc_t** out, const cube_voc_config* cfg, int device) {
+  if (!out || !cfg) return fail("null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail("no CUDA device: libcube_vocoder has no CPU path (%s)", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+  if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
+  if (cfg->arch != CUBE_VOC_HIFIGAN && cfg->arch != CUBE_VOC_PWN_STUDENT) return fail("unknown arch %d", cfg->arch);
+  if (cfg->arch == CUBE_VOC_HIFIGAN) {
+    if (cfg->n_ups < 1 || cfg->n_ups > CUBE_MAX_UPS) return fail("n_ups %d out of range", cfg->n_ups);
+    if (cfg->n_resblock_kernels < 1 || cfg->n_resblock_kernels > CUBE_MAX_RBK) return fail("n_resblock_kernels out of range");
+    if (cfg->resblock_type != 1 && cfg->resblock_type != 2) return fail("resblock must be 1 or 2");
+    if (cfg->upsample_initial_channel >> cfg->n_ups < 1) return fail("upsample_initial_channel too small");
+    for (int i = 0; i < cfg->n_ups; ++i) {
+      if (cfg->upsample_rates[i] < 1 || cfg->upsample_rates[i] > 8) return fail("upsample rate %d unsupported (1..8)", cfg->upsample_rates[i]);
+      if (cfg->upsample_kernel_sizes[i] < cfg->upsample_rates[i]) return fail("upsample kernel smaller than rate");
+    }
+    for (int j = 0; j < cfg->n_resblock_kernels; ++j) {
+      if (cfg->resblock_kernel_sizes[j] % 2 != 1) return fail("resblock kernel sizes must be odd");
+      if (cfg->n_dilations[j] < 1 || cfg->n_dilations[j] > CUBE_MAX_DIL) return fail("n_dilations out of range");
+    }
+  } else {
+    if (cfg->n_flows < 1 || cfg->n_flows > CUBE_MAX_FLOWS) return fail("n_flows out of range");
+    if (cfg->n_upsample < 1 || cfg->n_upsample > 4) return fail("n_upsample out of range");
+    if (cfg->gate_channels % 4) return fail("gate_channels must be a multiple of 4");
+  }
+  cube_voc* h = new cube_voc();
+  h->cfg = *cfg;
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail("cudaSetDevice(%d) failed", device); }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+    h->sm_count = prop.multiProcessorCount;
+    if (prop.major != 10) { delete h; return fail("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); }
+  }
+  *out = h;
+  return 0;
+}
+
+int cube_voc_load_weight(cube_voc_t* h, const char* name, const float* data, const int64_t* shape, int ndim) {
+  if (!h || !name || !data || (ndim > 0 && !shape)) return fail("null argument");
+  if (h->finalized) return fail("load_weight after finalize");
+  std::string n(name);
+  for (const char* pre : {"_generator.", "generator.", "module."})
+    if (n.rfind(pre, 0) == 0) n = n.substr(strlen(pre));
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  const int64_t ne = t.numel();
+  if (ne < 0 || ne > (1LL << 31)) return fail("bad shape for '%s'", name);
+  t.data.assign(data, data + ne);
+  h->host_w[n] = std::move(t);
+  return 0;
+}
+
+int cube_voc_finalize(cube_voc_t* h) {
+  if (!h) return fail("null handle");
+  if (h->finalized) return 0;
+  if (ensure_device(h)) return 1;
+  if (tables_ready()) return 1;
+  int rc = h->cfg.arch == CUBE_VOC_HIFIGAN ? finalize_hifigan(h) : finalize_student(h);
+  if (rc) return rc;
+  h->host_w.clear();
+  CU_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->finalized = true;
+  return 0;
+}
+
+int64_t cube_voc_out_len(const cube_voc_t* h, int64_t n_frames) {
+  if (!h || n_frames < 0) { fail("bad argument"); return -1; }
+  if (h->cfg.arch == CUBE_VOC_HIFIGAN) return n_frames == 0 ? 0 : hifigan_len(h->cfg, n_frames, h->cfg.n_ups);
+  int64_t T = n_frames;
+  for (int i = 0; i < h->cfg.n_upsample; ++i) T *= h->cfg.upsample_scales[i];
+  return T;
+}
+
+int cube_voc_forward(cube_voc_t* h, const float* mel, const int32_t* n_frames, const float* noise, float* wav,
+                     int16_t* wav_i16, int B, int64_t Fmax, cube_stream_t stream) {
+  if (!h) return fail("null handle");
+  if (!h->finalized) return fail("forward before finalize");
+  if (!mel || !wav) return fail("null mel/wav");
+  if (B < 1 || Fmax < 1) return fail("empty batch (B=%d, Fmax=%lld)", B, (long long)Fmax);
+  if (ensure_device(h)) return 1;
+  h->launches = 0;
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  h->prof.clear();
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->cfg.arch == CUBE_VOC_HIFIGAN) return forward_hifigan(h, mel, n_frames, wav, wav_i16, B, Fmax, st);
+  return forward_student(h, mel, n_frames, noise, wav, wav_i16, B, Fmax, st);
+}
+
+int cube_voc_forward_host(cube_voc_t* h, const float* mel, const int32_t* n_frames, const float* noise, float* wav,
+                          int16_t* wav_i16, int B, int64_t Fmax) {
+  if (!h) return fail("null handle");
+  if (!h->finalized) return fail("forward before finalize");
+  if (!mel || (!wav && !wav_i16)) return fail("null mel / no output buffer");
+  if (B < 1 || Fmax < 1) return fail("empty batch");
+  if (ensure_device(h)) return 1;
+  const int64_t T = cube_voc_out_len(h, Fmax);
+  const size_t mel_b = (size_t)B * h->cfg.num_mels * Fmax * sizeof(float);
+  const size_t wav_n = (size_t)B * T;
+  if (grow(&h->d_mel, &h->d_mel_cap, mel_b) || grow(&h->d_wav, &h->d_wav_cap, wav_n * sizeof(float))) return 1;
+  if (wav_i16 && grow(&h->d_wav16, &h->d_wav16_cap, wav_n * sizeof(int16_t))) return 1;
+  cudaStream_t st = h->own_stream;
+  CU_TRY(cudaMemcpyAsync(h->d_mel, mel, mel_b, cudaMemcpyHostToDevice, st));
+  if (noise) {
+    if (grow(&h->d_noise, &h->d_noise_cap, wav_n * sizeof(float))) return 1;
+    CU_TRY(cudaMemcpyAsync(h->d_noise, noise, wav_n * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  if (cube_voc_forward(h, h->d_mel, n_frames, noise ? h->d_noise : nullptr, h->d_wav, wav_i16 ? h->d_wav16 : nullptr, B, Fmax, st)) return 1;
+  if (wav) CU_TRY(cudaMemcpyAsync(wav, h->d_wav, wav_n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (wav_i16) CU_TRY(cudaMemcpyAsync(wav_i16, h->d_wav16, wav_n * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int cube_voc_get_cond(cube_voc_t* h, float* c_up, int B, int64_t Tmax, cube_stream_t stream) {
+  if (!h || !c_up) return fail("null argument");
+  if (h->cfg.arch != CUBE_VOC_PWN_STUDENT) return fail("get_cond is only defined for the IAF student");
+  if (B != h->last_B || Tmax != h->last_T) return fail("geometry differs from the last forward");
+  auto it = h->ws.find("c_up");
+  if (it == h->ws.end()) return fail("no forward has run");
+  CU_TRY(cudaMemcpyAsync(c_up, it->second.p, (size_t)B * h->cfg.num_mels * Tmax * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int64_t cube_voc_last_launches(const cube_voc_t* h) { return h ? h->launches : -1; }
+
+int64_t cube_voc_workspace_bytes(const cube_voc_t* h) {
+  if (!h) return -1;
+  int64_t n = 0;
+  for (auto& kv : h->ws) n += (int64_t)kv.second.bytes;
+  return n;
+}
+
+int cube_voc_set_profile(cube_voc_t* h, int on) {
+  if (!h) return fail("null handle");
+  h->profile = on != 0;
+  return 0;
+}
+
+int cube_voc_get_profile(cube_voc_t* h, char* names, float* ms, int cap) {
+  if (!h || !names || !ms) { fail("null argument"); return -1; }
+  std::map<std::string, float> agg;
+  std::vector<std::string> order;
+  for (auto& r : h->prof) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) { fail("profile event sync failed"); return -1; }
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    if (!agg.count(r.name)) order.push_back(r.name);
+    agg[r.name] += t;
+  }
+  int n = 0;
+  for (auto& k : order) {
+    if (n >= cap) break;
+    snprintf(names + (size_t)n * 64, 64, "%s", k.c_str());
+    ms[n] = agg[k];
+    ++n;
+  }
+  return n;
+}
+
+void cube_voc_destroy(cube_voc_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (void* p : h->dev_allocs) cudaFree(p);
+  for (auto& kv : h->ws) if (kv.second.p) cudaFree(kv.second.p);
+  if (h->d_lens) cudaFree(h->d_lens);
+  if (h->d_mel) cudaFree(h->d_mel);
+  if (h->d_noise) cudaFree(h->d_noise);
+  if (h->d_wav) cudaFree(h->d_wav);
+  if (h->d_wav16) cudaFree(h->d_wav16);
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+// ---- heads ----
+#define HEAD_PROLOGUE(n)                        \
+  if ((n) < 0) return fail("negative length");  \
+  if ((n) == 0) return 0;                       \
+  if (tables_ready()) return 1;
+
+int cube_mulaw_encode(const float* x, int64_t* q, int64_t n, cube_stream_t s) {
+  HEAD_PROLOGUE(n);
+  if (!x || !q) return fail("null argument");
+  mulaw_encode_kernel<<<head_grid(n), 256, 0, (cudaStream_t)s>>>(x, (long long*)q, n);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+int cube_mulaw_decode(const int64_t* q, float* x, int64_t n, cube_stream_t s) {
+  HEAD_PROLOGUE(n);
+  if (!x || !q) return fail("null argument");
+  mulaw_decode_kernel<<<head_grid(n), 256, 0, (cudaStream_t)s>>>((const long long*)q, x, n);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+int cube_raw_encode(const float* x, int64_t* q, int64_t n, cube_stream_t s) {
+  HEAD_PROLOGUE(n);
+  if (!x || !q) return fail("null argument");
+  raw_encode_kernel<<<head_grid(n), 256, 0, (cudaStream_t)s>>>(x, (long long*)q, n);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+int cube_raw_decode(const int64_t* q, float* x, int64_t n, cube_stream_t s) {
+  HEAD_PROLOGUE(n);
+  if (!x || !q) return fail("null argument");
+  raw_decode_kernel<<<head_grid(n), 256, 0, (cudaStream_t)s>>>((const long long*)q, x, n);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+int cube_mol_sample(const float* y, const float* u_mix, const float* u_x, float* x, int64_t n, int nr_mix,
+                    float log_scale_min, float temperature, cube_stream_t s) {
+  HEAD_PROLOGUE(n);
+  if (!y || !u_mix || !u_x || !x) return fail("null argument");
+  if (nr_mix < 1) return fail("nr_mix < 1");
+  mol_sample_kernel<<<head_grid(n), 256, 0, (cudaStream_t)s>>>(y, u_mix, u_x, x, n, nr_mix, log_scale_min, temperature);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+int cube_gaussian_sample(const float* y, const float* eps, float* x, int64_t n, cube_stream_t s) {
+  HEAD_PROLOGUE(n);
+  if (!y || !eps || !x) return fail("null argument");
+  gaussian_sample_kernel<<<head_grid(n), 256, 0, (cudaStream_t)s>>>(y, eps, x, n);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+int cube_categorical_sample(const float* logits, const float* u, int64_t* idx, int64_t n, int C, cube_stream_t s) {
+  HEAD_PROLOGUE(n);
+  if (!logits || !u || !idx) return fail("null argument");
+  if (C < 1) return fail("C < 1");
+  categorical_sample_kernel<<<head_grid(n * 32), 256, 0, (cudaStream_t)s>>>(logits, u, (long long*)idx, n, C);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+int cube_wav_to_int16(const float* wav, int16_t* out, int64_t n, cube_stream_t s) {
+  if (n < 0) return fail("negative length");
+  if (n == 0) return 0;
+  if (!wav || !out) return fail("null argument");
+  wav_to_int16_kernel<<<head_grid(n), 256, 0, (cudaStream_t)s>>>(wav, out, n);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
