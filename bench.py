@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the vocoder hot path (contract: see the task statement / DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cube|reference] [--workload pwn|hifigan]
+
+One "step" = one pass of the hot path over one batch of synthetic mel.  Default workload is
+BASELINE.json configs[1]: batch=8 x 10 s utterances, 80-bin synthetic mel, ParallelWaveNet (ClariNet
+IAF student) vocoder, per GPU (weak scaling: every rank synthesises its own batch, no data-path
+collective).  ``--workload hifigan`` runs configs[2] (batch=64 x 10 s, HiFi-GAN generator).
+
+Prints ONE JSON line (rank 0).  ``value`` is device-timed (CUDA events, inputs resident in HBM);
+``e2e`` goes through the host-buffer C-ABI call with H2D/D2H inside the timed region.
+``--impl reference`` times the CPU oracle port (the reference ships no runnable CPU code for the
+student - weights only - and /root/reference is not on the GPU box) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SR = 22050.0
+WORKLOADS = {
+    # name: (arch, batch per GPU, frames, description)
+    "pwn": ("student", 8, 862, "BASELINE configs[1]: batch=8 x 10 s (F=862, T=220672), 80-bin synthetic mel, ParallelWaveNet student"),
+    "hifigan": ("hifigan", 64, 919, "BASELINE configs[2]: batch=64 x 10 s (F=919), HiFi-GAN generator (neb-noft rates [3,5,4,4])"),
+}
+# algorithmic work per output sample of the dominant kernel (DESIGN.md "Measurement")
+GATE_FLOPS = 2.0 * (2 * 256 * 128 * 3 + 2 * 256 * 80)     # gated dilated conv + conditioning 1x1
+GATE_BYTES = 4.0 * (128 + 80 + 256)                        # read h, read c_up, write o (fp32)
+HIFI_FLOPS_PER_SAMPLE = 1022.2e3                           # SURVEY 8(d), neb-noft rates
+HIFI_BYTES_PER_SAMPLE = 9021.0
+PWN_FLOPS_PER_SAMPLE = 25.63e6
+PWN_BYTES_PER_SAMPLE = 103609.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_weights(arch):
+    """Shipped checkpoints when staged under oracle/_ref/weights, else seeded random weights of the same
+    architecture (throughput does not depend on the values)."""
+    from oracle import clarinet_ref as C, hifigan_ref as H
+    W = os.path.join(ROOT, "oracle", "_ref", "weights")
+
+    def ld(n):
+        p = os.path.join(W, n)
+        return torch.load(p, map_location="cpu", weights_only=False) if os.path.exists(p) else None
+
+    if arch == "student":
+        s, t = ld("pnn_vocoder.network"), ld("nn_vocoder.network")
+        if s is not None and t is not None:
+            return (s, t), "shipped pnn_vocoder.network + nn_vocoder.network upsampler"
+        return (C.random_state_dict("student", 1), C.random_state_dict("teacher", 2)), "seeded random-init weights (shipped checkpoints not staged)"
+    g = ld("g_00600000")
+    cfg = dict(H.CONFIG_NEB)
+    if g is not None:
+        return (g["generator"], cfg), "shipped g_00600000"
+    return (H.random_state_dict(cfg, seed=1), cfg), "seeded random-init weights (shipped checkpoint not staged)"
+
+
+def synth_inputs(arch, B, F, seed):
+    from oracle import clarinet_ref as C, hifigan_ref as H
+    if arch == "student":
+        mel = C.synthetic_mel01(B, F, seed=seed)
+        z = torch.randn(B, 1, F * 256, generator=torch.Generator().manual_seed(seed + 1))
+        return mel, z
+    return H.synthetic_mel(B, F, seed=seed), None
+
+
+def best_cpu_threads(arch, weights):
+    """torch's CPU convs on these small tensors get SLOWER past a few dozen threads (128 threads on the
+    GPU box ran 300x slower than 8): sweep upward from 8 and keep the fastest."""
+    ncpu = os.cpu_count() or 1
+    best, best_rate = min(8, ncpu), 0.0
+    t = min(8, ncpu)
+    frames = 12 if arch == "student" else 48
+    while True:
+        rate, _, dt = cpu_oracle_rate(arch, weights, frames, t)
+        if rate > best_rate:
+            best, best_rate = t, rate
+        elif rate < 0.7 * best_rate:
+            break
+        if t >= ncpu or dt > 20:
+            break
+        t = min(ncpu, t * 2)
+    return best, best_rate
+
+
+def cpu_oracle_rate(arch, weights, frames, threads):
+    """Time the CPU oracle port on B=1 x `frames`; returns (samples/s, samples, seconds)."""
+    from oracle import clarinet_ref as C, hifigan_ref as H
+    torch.set_num_threads(threads)
+    mel, z = synth_inputs(arch, 1, frames, seed=99)
+    t0 = time.perf_counter()
+    if arch == "student":
+        y = C.vocode_student(weights[0], weights[1], mel, z)
+    else:
+        y = H.generator_forward(weights[0], weights[1], mel)
+    dt = time.perf_counter() - t0
+    return y.shape[-1] / dt, int(y.shape[-1]), dt
+
+
+def run_reference(args, arch, B, F, desc, rank, world):
+    """--impl reference: the CPU path on the host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    weights, wdesc = load_weights(arch)
+    threads, rate = best_cpu_threads(arch, weights)                                       # calibration
+    budget = min(12.0, 150.0 / max(1, args.steps + args.warmup))
+    hop = 256 if arch == "student" else 240
+    frames = int(max(8, min(F, rate * budget / hop)))
+    for _ in range(args.warmup):
+        cpu_oracle_rate(arch, weights, frames, threads)
+    tot_s, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        _, n, dt = cpu_oracle_rate(arch, weights, frames, threads)
+        tot_s += n; tot_t += dt
+    val = tot_s / tot_t
+    sample = (f"B=1 x {frames} frames ({frames * hop / SR:.2f} s of audio) per step of the same synthetic workload; oracle port "
+              f"(torch CPU fp32), {threads} threads = fastest of a sweep on a {os.cpu_count()}-core host")
+    line = {
+        "impl": "reference", "metric": "audio samples/sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic; " + wdesc,
+        "rtf": val / SR, "config": {"workload": desc},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cube", choices=["cube", "reference"])
+    ap.add_argument("--workload", default="pwn", choices=list(WORKLOADS))
+    ap.add_argument("--math", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug)")
+    ap.add_argument("--frames", type=int, default=0, help="override frames per utterance (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    arch, B, F, desc = WORKLOADS[args.workload]
+    B = args.batch or B
+    F = args.frames or F
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, arch, B, F, desc, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    import tts_cube_b200 as cube
+    from tts_cube_b200 import _lib
+    assert torch.cuda.is_available(), "bench.py --impl cube needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    math = {"auto": _lib.MATH_FP32_SIMT, "simt": _lib.MATH_FP32_SIMT, "tc": _lib.MATH_TC_SPLIT16}[args.math]
+    if args.math == "auto" and os.environ.get("CUBE_MATH", "") == "tc":
+        math = _lib.MATH_TC_SPLIT16
+    weights, wdesc = load_weights(arch)
+    if arch == "student":
+        voc = cube.ParallelWaveNetVocoder(weights[0], weights[1], math=math).to(dev)
+    else:
+        voc = cube.CubeGenerator(weights[1], math=math).to(dev)
+        voc.load_state_dict(weights[0])
+    T = voc.out_len(F)
+    samples_per_step = B * T
+    # two input sets, alternated, resident in HBM; the per-step working set (activations, GBs) is far
+    # larger than the 126 MB L2, so nothing survives in L2 from one step to the next
+    sets = []
+    for k in range(2):
+        mel, z = synth_inputs(arch, B, F, seed=1234 + 10 * rank + k)
+        sets.append((mel.to(dev), z.to(dev) if z is not None else None, mel.pin_memory(), z.pin_memory() if z is not None else None))
+    handle = voc._ensure()
+
+    def step(k):
+        mel, z, _, _ = sets[k & 1]
+        return voc(mel, z) if arch == "student" else voc(mel)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for k in range(args.warmup):
+            y = step(k)
+        barrier()
+        handle.set_profile(True)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches, prof = 0, {}
+        barrier()
+        ev0.record()
+        for k in range(args.steps):
+            y = step(k)
+            launches += handle.launches()
+            if k == args.steps - 1:
+                pass
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        prof = handle.get_profile()       # per-layer-class device time of the LAST timed step
+        n_launch_last = handle.launches()
+        handle.set_profile(False)
+        clocks = sampler.stop() if rank == 0 else None
+        # ---- end to end through the host-buffer C-ABI call (H2D + forward + D2H per step) ----
+        out_host = torch.empty(B, T, dtype=torch.float32).pin_memory()
+        for k in range(2):
+            _, _, mh, zh = sets[k & 1]
+            voc.forward_host(mh, zh, out=out_host) if arch == "student" else voc.forward_host(mh, out=out_host)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            _, _, mh, zh = sets[k & 1]
+            voc.forward_host(mh, zh, out=out_host) if arch == "student" else voc.forward_host(mh, out=out_host)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+    t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    assert bool(torch.isfinite(y).all()), "non-finite audio"
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    total = samples_per_step * world * args.steps
+    value = total / (ms / 1e3)
+    e2e_val = total / (e2e_ms / 1e3)
+    h2d = sets[0][2].numel() * 4 + (sets[0][3].numel() * 4 if sets[0][3] is not None else 0)
+    d2h = out_host.numel() * 4
+    # ---- roofline of the dominant kernel (device time of its launches inside the last timed step) ----
+    if arch == "student":
+        dom = "gate"
+        nlaunch = sum(int(weights[0][k].shape[0] > 0) for k in weights[0] if k.endswith("filter_conv.conv.bias"))
+        dom_ms = prof.get(dom, 0.0)
+        flops_launch = GATE_FLOPS * samples_per_step
+        ach = flops_launch * nlaunch / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else None
+        roof = {"kernel": "conv_tile_kernel (gated dilated conv + conditioning 1x1, EPI_GATE)" if math == 0 else "tc gate",
+                "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                "frac": (ach / pk["tf_sust"]) if ach else None, "traffic": None,
+                "launches_per_step": nlaunch, "avg_launch_ms": dom_ms / max(1, nlaunch),
+                "algorithmic_flops_per_launch": flops_launch, "algorithmic_bytes_per_launch": GATE_BYTES * samples_per_step,
+                "share_of_step": dom_ms / (ms / args.steps) if ms > 0 else None,
+                "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
+                "math": "fp32 FFMA (no tensor cores)" if math == 0 else "tcgen05 split-fp16 x3"}
+        whole = {"flops_per_sample": PWN_FLOPS_PER_SAMPLE, "bytes_per_sample": PWN_BYTES_PER_SAMPLE}
+    else:
+        dom = "rb_conv1"
+        dom_ms = prof.get("rb_conv1", 0.0) + prof.get("rb_conv2", 0.0)
+        nlaunch = 72
+        # resblock convs: 95 % of layer-wise bytes, 96 % of FLOPs
+        by = 0.95 * HIFI_BYTES_PER_SAMPLE * samples_per_step
+        ach = by / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else None
+        roof = {"kernel": "conv_tile_kernel (ResBlock dilated convs, fused lrelu/bias/residual)", "bound": "hbm",
+                "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": (ach / pk["hbm"]) if ach else None, "traffic": None,
+                "launches_per_step": nlaunch, "avg_launch_ms": dom_ms / nlaunch, "algorithmic_bytes_per_launch": by / nlaunch,
+                "share_of_step": dom_ms / (ms / args.steps) if ms > 0 else None, "peak_source": pk["src"] + " copy bandwidth",
+                "tensor_frac": 0.96 * HIFI_FLOPS_PER_SAMPLE * samples_per_step / (dom_ms / 1e3) / 1e12 / pk["tf_sust"] if dom_ms > 0 else None}
+        whole = {"flops_per_sample": HIFI_FLOPS_PER_SAMPLE, "bytes_per_sample": HIFI_BYTES_PER_SAMPLE}
+    whole["hbm_frac_whole_path"] = whole["bytes_per_sample"] * value / world / 1e9 / pk["hbm"]
+    whole["tensor_frac_whole_path"] = whole["flops_per_sample"] * value / world / 1e12 / pk["tf_sust"]
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads, rate = best_cpu_threads(arch, weights)
+        hop = 256 if arch == "student" else 240
+        frames = int(max(8, min(F, rate * 15.0 / hop)))
+        r2, n, dt = cpu_oracle_rate(arch, weights, frames, threads)
+        cpu = {"value": r2, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"B=1 x {frames} frames ({n} samples, {dt:.1f} s of CPU) of the same synthetic workload; oracle port, torch CPU fp32, {threads} threads"}
+
+    line = {
+        "metric": "audio samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic; " + wdesc,
+        "rtf": value / SR, "rtf_per_gpu": value / SR / world,
+        "config": {"workload": desc, "batch_per_gpu": B, "frames": F, "samples_per_utterance": T, "parallelism": f"dp{world} (utterance shards, no data-path collective)",
+                   "l2": "per-step activation working set (GBs) >> 126 MB L2; two input sets alternated",
+                   "math": "fp32_simt" if math == 0 else "tc_split_fp16x3"},
+        "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                "api": "ParallelWaveNetVocoder.forward_host -> cube_voc_forward_host (pinned host buffers)" if arch == "student" else "CubeGenerator.forward_host -> cube_voc_forward_host"},
+        "gpu_launches": launches, "launches_per_step": n_launch_last,
+        "roofline": roof, "whole_path": whole, "layer_ms_last_step": prof, "cpu_baseline": cpu, "clocks": clocks,
+        "workspace_bytes": handle.workspace_bytes(), "lib": cube.build_info(),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -49,9 +49,10 @@ def test_hifigan_golden_trained(dev, neb):
     ref16 = d["wav_int16"].astype(np.int32)
     got16 = w16.cpu().numpy().astype(np.int32)
     assert np.abs(got16 - ref16).max() <= 1
-    frac = np.abs(d["wav"].squeeze(1) * 32767 - np.round(d["wav"].squeeze(1) * 32767))
-    safe = frac > 32767 * 4 * err + 1e-3
-    assert np.array_equal(got16[~(~safe)], ref16[safe]) if safe.any() else True
+    v = d["wav"].squeeze(1).astype(np.float64) * 32767
+    mism = got16 != ref16                                     # only where truncation sits on an integer edge
+    assert mism.mean() <= 4 * 32767 * err + 1e-3              # a flip needs v within 32767*err of an integer
+    assert np.all(np.abs(v - np.round(v))[mism] <= 32767 * err + 1e-3)
     # and exactly int16(wav*32767) of the wav it returned (cube/api.py:65)
     assert torch.equal(w16.cpu(), H.wav_to_int16(wav.cpu()).squeeze(1))
 
@@ -85,7 +86,8 @@ def test_hifigan_config_v1_random_weights_ragged(dev):
     assert y.shape == ref.shape
     assert float((y - ref).abs().max()) <= TOL
     for b, f in enumerate(frames):
-        assert float(y[b, 0, H.out_len(cfg, f):].abs().max()) == 0.0
+        tail = y[b, 0, H.out_len(cfg, f):]
+        assert tail.numel() == 0 or float(tail.abs().max()) == 0.0
 
 
 def test_hifigan_edge_cases(dev):
@@ -153,9 +155,12 @@ def test_hifigan_full_size_properties(dev, neb):
 
 
 # ------------------------------------------------ Path C ------------------------------------------------
-def _student(ssd, tsd, dev):
+def _student(ssd, tsd, dev, math=0):
     import tts_cube_b200 as cube
-    return cube.ParallelWaveNetVocoder(ssd, tsd).to(dev).eval()
+    return cube.ParallelWaveNetVocoder(ssd, tsd, math=math).to(dev).eval()
+
+
+MATHS = [pytest.param(0, id="fp32_simt"), pytest.param(1, id="tcgen05_split16")]
 
 
 def test_upsample2_golden(dev):
@@ -171,29 +176,35 @@ def test_upsample2_golden(dev):
     assert float(np.abs(c - d["c_up"]).max()) <= 1e-5
 
 
-def test_student_small_random_weights(dev):
+@pytest.mark.parametrize("math", MATHS)
+def test_student_small_random_weights(dev, math):
     ssd, tsd = C.random_state_dict("student", 3, blocks=[7, 2, 1, 3]), C.random_state_dict("teacher", 4, blocks=[1])
     mel = C.synthetic_mel01(2, 5, seed=2)
     z = torch.randn(2, 1, 5 * 256, generator=torch.Generator().manual_seed(1))
     ref = C.vocode_student(ssd, tsd, mel, z)
-    v = _student(ssd, tsd, dev)
+    v = _student(ssd, tsd, dev, math)
     with torch.no_grad():
         x = v(mel.to(dev), z.to(dev)).cpu()
+    err = float((x - ref).abs().max())
+    print(f"student small math={math}: max-abs {err:.3e} (peak {float(ref.abs().max()):.2f})")
     assert float(ref.abs().max()) > 0.05
-    assert float((x - ref).abs().max()) <= TOL
-    assert float((x - ref).abs().max()) <= 5e-5
+    assert err <= TOL
+    assert err <= 5e-5   # both math modes sit near fp32 round-off
 
 
-def test_student_shipped_weights(dev, clarinet_weights):
+@pytest.mark.parametrize("math", MATHS)
+def test_student_shipped_weights(dev, clarinet_weights, math):
     ssd, tsd, trained = clarinet_weights
     mel = C.synthetic_mel01(2, 8, seed=8)
     z = torch.randn(2, 1, 8 * 256, generator=torch.Generator().manual_seed(9))
     ref = C.vocode_student(ssd, tsd, mel, z)
-    v = _student(ssd, tsd, dev)
+    v = _student(ssd, tsd, dev, math)
     with torch.no_grad():
         x = v(mel.to(dev), z.to(dev)).cpu()
+    err = float((x - ref).abs().max())
+    print(f"student shipped={trained} math={math}: max-abs {err:.3e} (peak {float(ref.abs().max()):.2f})")
     assert float(ref.abs().max()) > 0.1
-    assert float((x - ref).abs().max()) <= TOL
+    assert err <= TOL
     if trained:
         d = load_golden("clarinet_regress.npz")
         with torch.no_grad():
@@ -201,11 +212,12 @@ def test_student_shipped_weights(dev, clarinet_weights):
         assert float(np.abs(xr - d["wav"]).max()) <= TOL
 
 
-def test_student_ragged_and_causal(dev):
+@pytest.mark.parametrize("math", MATHS)
+def test_student_ragged_and_causal(dev, math):
     ssd, tsd = C.random_state_dict("student", 3, blocks=[6, 1, 1, 2]), C.random_state_dict("teacher", 4, blocks=[1])
     mel = C.synthetic_mel01(2, 6, seed=12)
     z = torch.randn(2, 1, 6 * 256, generator=torch.Generator().manual_seed(3))
-    v = _student(ssd, tsd, dev)
+    v = _student(ssd, tsd, dev, math)
     mel_pad = mel.clone()
     mel_pad[1, :, 4:] = 9.0
     with torch.no_grad():
@@ -221,7 +233,8 @@ def test_student_ragged_and_causal(dev):
     assert torch.equal(v.forward_host(mel.pin_memory(), z.pin_memory()), d_)
 
 
-def test_student_full_length_properties(dev):
+@pytest.mark.parametrize("math", MATHS)
+def test_student_full_length_properties(dev, math):
     """Config-2 length (10 s, T=220672) with a shallow student: finite, deterministic, causal (a change
     of z at sample s never alters samples < s) and batch items independent."""
     ssd, tsd = C.random_state_dict("student", 3, blocks=[6, 1]), C.random_state_dict("teacher", 4, blocks=[1])
@@ -229,7 +242,7 @@ def test_student_full_length_properties(dev):
     mel = C.synthetic_mel01(2, F, seed=5)
     g = torch.Generator().manual_seed(11)
     z = torch.randn(2, 1, F * 256, generator=g)
-    v = _student(ssd, tsd, dev)
+    v = _student(ssd, tsd, dev, math)
     with torch.no_grad():
         a = v(mel.to(dev), z.to(dev))
         z2 = z.clone()
@@ -243,6 +256,11 @@ def test_student_full_length_properties(dev):
     n = 3 * 256
     ref = C.vocode_student(ssd, tsd, mel[:1, :, :8], z[:1, :, : 8 * 256])
     assert float((a[0, 0, :n].cpu() - ref[0, 0, :n]).abs().max()) <= TOL
+    # and the tensor-core path against the fp32 SIMT path over the WHOLE 10 s utterance
+    if math == 1:
+        with torch.no_grad():
+            s_ = _student(ssd, tsd, dev, 0)(mel.to(dev), z.to(dev))
+        assert float((a - s_).abs().max()) <= 1e-4
 
 
 # ------------------------------------------------ heads ------------------------------------------------

@@ -73,11 +73,14 @@ __global__ void __launch_bounds__(256, (TM >= 16 ? 1 : 2)) conv_tile_kernel(cons
   const int b = blockIdx.z / p.nphase, ph = blockIdx.z - b * p.nphase;
   const float* __restrict__ Wph = p.W + (long long)ph * p.w_phase_stride;
 
-  float acc[TM][TN];
+  // accumulators as (even row, odd row) pairs: the inner product runs on packed fma.rn.f32x2
+  // (FFMA2) - on sm_100 a 3-register FFMA issues every other cycle per SMSP, FFMA2 restores the
+  // full 128 FMA/clk/SM rate.
+  float2 acc2[TM / 2][TN];
 #pragma unroll
-  for (int i = 0; i < TM; ++i)
+  for (int i = 0; i < TM / 2; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc2[i][j] = make_float2(0.f, 0.f);
 
   int kbase = 0;
   for (int s = 0; s < p.nseg; ++s) {
@@ -133,18 +136,22 @@ __global__ void __launch_bounds__(256, (TM >= 16 ? 1 : 2)) conv_tile_kernel(cons
         const float* xrow = xbase + ci * XP;
         const float* wrow = wbase + ci * taps * BM;
         for (int t = 0; t < taps; ++t) {
-          float w[TM], x[TN];
+          float2 w2[TM / 2];
+          float x[TN];
 #pragma unroll
           for (int i = 0; i < TM; i += 4) {
             const float4 w4 = *reinterpret_cast<const float4*>(wrow + t * BM + i);
-            w[i] = w4.x; w[i + 1] = w4.y; w[i + 2] = w4.z; w[i + 3] = w4.w;
+            w2[i / 2] = make_float2(w4.x, w4.y);
+            w2[i / 2 + 1] = make_float2(w4.z, w4.w);
           }
 #pragma unroll
           for (int j = 0; j < TN; ++j) x[j] = xrow[t * tapstride + 32 * j];
 #pragma unroll
-          for (int i = 0; i < TM; ++i)
+          for (int j = 0; j < TN; ++j) {
+            const float2 xx = make_float2(x[j], x[j]);
 #pragma unroll
-            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(w[i], x[j], acc[i][j]);
+            for (int i = 0; i < TM / 2; ++i) acc2[i][j] = __ffma2_rn(w2[i], xx, acc2[i][j]);
+          }
         }
       }
     }
@@ -152,6 +159,7 @@ __global__ void __launch_bounds__(256, (TM >= 16 ? 1 : 2)) conv_tile_kernel(cons
   }
 
   // ---------------------------------- epilogue ----------------------------------
+#define ACC(i, j) (((i) & 1) ? acc2[(i) >> 1][j].y : acc2[(i) >> 1][j].x)
   const int olen = p.out_lens ? min(p.out_lens[b], p.L_out) : p.L_out;
   const int ooff = p.ooff[ph];
   const int mbase = m0 + wm * TM;
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(256, (TM >= 16 ? 1 : 2)) conv_tile_kernel(cons
       for (int i = 0; i < TM; ++i) {
         const int m = mbase + i;
         if (m >= p.M) break;
-        float y = acc[i][j] + __ldg(p.bias + m);
+        float y = ACC(i, j) + __ldg(p.bias + m);
         if (p.post == POST_RELU) y = fmaxf(y, 0.f);
         else if (p.post == POST_TANH) y = tanhf(y);
         p.out[(long long)b * p.out_bstride + (long long)m * p.L_out + t] = valid ? y : 0.f;
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(256, (TM >= 16 ? 1 : 2)) conv_tile_kernel(cons
         const int m = mbase + i;
         if (m >= p.M) break;
         const long long off = (long long)m * p.L_out + t;
-        float y = acc[i][j] + __ldg(p.bias + m) + p.res[(long long)b * p.res_bstride + off];
+        float y = ACC(i, j) + __ldg(p.bias + m) + p.res[(long long)b * p.res_bstride + off];
         if (!valid) y = 0.f;
         if (p.out) p.out[(long long)b * p.out_bstride + off] = y;
         if (p.acc_mode != ACC_NONE) {
@@ -193,8 +201,8 @@ __global__ void __launch_bounds__(256, (TM >= 16 ? 1 : 2)) conv_tile_kernel(cons
       for (int i = 0; i < TM; i += 2) {
         const int m = mbase + i;
         if (m >= p.M) break;
-        const float f = acc[i][j] + __ldg(p.bias + m);
-        const float g = acc[i + 1][j] + __ldg(p.bias + m + 1);
+        const float f = acc2[i >> 1][j].x + __ldg(p.bias + m);
+        const float g = acc2[i >> 1][j].y + __ldg(p.bias + m + 1);
         const float y = tanhf(f) * sigmoid_acc(g);
         p.out[(long long)b * p.out_bstride + (long long)(m >> 1) * p.L_out + t] = valid ? y : 0.f;
       }
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(256, (TM >= 16 ? 1 : 2)) conv_tile_kernel(cons
       for (int i = 0; i < TM; ++i) {
         const int m = mbase + i;
         if (m >= p.M) break;
-        const float v = acc[i][j] + __ldg(p.bias + m);
+        const float v = ACC(i, j) + __ldg(p.bias + m);
         if (m < p.Mh) {
           const long long off = (long long)m * p.L_out + t;
           const float y = (p.res[(long long)b * p.res_bstride + off] + v) * p.scale;
@@ -216,6 +224,7 @@ __global__ void __launch_bounds__(256, (TM >= 16 ? 1 : 2)) conv_tile_kernel(cons
       }
     }
   }
+#undef ACC
 }
 
 // ------------------------------------------------------------------------------------------

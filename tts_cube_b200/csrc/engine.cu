@@ -16,6 +16,7 @@
 #include "../../include/cube_vocoder.h"
 #include "conv_simt.cuh"
 #include "heads.cuh"
+#include "tc_conv.cuh"
 
 #define CUBE_VERSION "0.1.0"
 
@@ -58,6 +59,15 @@ struct PackedConv {
 
 struct ProfRec { std::string name; cudaEvent_t a, b; };
 
+// One dense layer in tcgen05 form (tc_conv.cuh): swizzled split-fp16 weight images.
+struct TcPacked {
+  __half* Wimg = nullptr;
+  float* inv_scale = nullptr;
+  float* bias = nullptr;
+  int N = 0, n_tiles = 0, nchunks_total = 0, nseg = 0;
+  tc::TcSeg seg[2];
+};
+
 }  // namespace cube
 
 using namespace cube;
@@ -91,7 +101,11 @@ struct cube_voc {
   std::vector<PackedConv> ups;
   std::vector<std::vector<PackedConv>> rb_c1, rb_c2;  // [resblock idx][dilation idx]
   // ClariNet packed layers
-  struct Flow { PackedConv front, final1, final3; std::vector<PackedConv> gate, resskip; };
+  struct Flow {
+    PackedConv front, final1, final3;
+    std::vector<PackedConv> gate, resskip;
+    std::vector<TcPacked> tc_gate, tc_resskip;
+  };
   std::vector<Flow> flows;
   struct Up2 { float w[192]; float bias; int s; };
   std::vector<Up2> up2;
@@ -224,6 +238,79 @@ static int pack_small(cube_voc* h, const std::string& base, int M, int C, int K,
   }
   if (dev_upload(h, P, &pc->W)) return 1;
   return dev_upload(h, B, &pc->bias);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 weight packing: dense [N][nchunks*64] (chunk order = the kernel's K order, zero padded) ->
+// per-row power-of-two scaling, fp16 hi/lo split, 128B-swizzled [BN x 64] smem images.
+// ------------------------------------------------------------------------------------------------
+static int dev_upload_bytes(cube_voc* h, const void* src, size_t bytes, void** out) {
+  void* d = nullptr;
+  CU_TRY(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
+  CU_TRY(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+  h->dev_allocs.push_back(d);
+  *out = d;
+  return 0;
+}
+
+static int pack_tc(cube_voc* h, const std::vector<float>& dense, const std::vector<float>& bias, int N, int nchunks,
+                   TcPacked* out) {
+  using namespace tc;
+  if (N % BN) return fail("tensor-core path needs N %% %d == 0 (got %d)", BN, N);
+  const int Kp = nchunks * BK;
+  out->N = N; out->n_tiles = N / BN; out->nchunks_total = nchunks;
+  std::vector<__half> img((size_t)out->n_tiles * nchunks * 2 * BN * BK);
+  std::vector<float> inv(N);
+  for (int n = 0; n < N; ++n) {
+    float mx = 0.f;
+    for (int k = 0; k < Kp; ++k) mx = std::max(mx, fabsf(dense[(size_t)n * Kp + k]));
+    int e = 0;
+    if (mx > 0.f) { int ex; frexpf(mx, &ex); e = 12 - ex; }   // mx*2^e in [2^11, 2^12)
+    const float sc = ldexpf(1.f, e);
+    inv[n] = ldexpf(1.f, -e);
+    const int nt = n / BN, r = n % BN;
+    for (int ch = 0; ch < nchunks; ++ch)
+      for (int kk = 0; kk < BK; ++kk) {
+        const float w = dense[(size_t)n * Kp + ch * BK + kk] * sc;
+        const __half hi = __float2half_rn(w);
+        const __half lo = __float2half_rn(w - __half2float(hi));
+        const size_t off = (size_t)(r / 8) * 512 + (size_t)(r % 8) * 64 + (size_t)(((kk / 8) ^ (r % 8)) * 8) + (kk % 8);
+        const size_t base = ((size_t)(nt * nchunks + ch) * 2) * (BN * BK);
+        img[base + off] = hi;
+        img[base + (size_t)BN * BK + off] = lo;
+      }
+  }
+  void* d;
+  if (dev_upload_bytes(h, img.data(), img.size() * sizeof(__half), &d)) return 1;
+  out->Wimg = (__half*)d;
+  if (dev_upload(h, inv, &out->inv_scale)) return 1;
+  return dev_upload(h, bias, &out->bias);
+}
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// fp16 planes [2][B][T][C] channels-last -> 3-D tensor map (C, T, 2B), box (64, 128, 1), 128B swizzle,
+// out-of-bounds rows/channels read as zero (that IS the conv zero padding).
+static int make_tmap_hl16(CUtensorMap* tm, const __half* base, int B, int T, int C) {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled not available from the driver");
+    fn = (PFN_tmapEncodeTiled)p;
+  }
+  if (C % 8) return fail("channels-last fp16 tensor needs C %% 8 == 0 (got %d)", C);
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)(2 * B)};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2};
+  cuuint32_t box[3] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for [2*%d][%d][%d]", (int)r, B, T, C);
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -427,6 +514,41 @@ static int finalize_student(cube_voc* h) {
         for (int cc = 0; cc < G; ++cc) P2[(size_t)cc * pr.Mpad + R + m] = ws.data[(size_t)m * G + cc];
       }
       if (dev_upload(h, P2, &pr.W) || dev_upload(h, B2, &pr.bias)) return 1;
+      if (c.math == CUBE_MATH_TC_SPLIT16) {
+        using namespace tc;
+        if (R != 128 || S != 128 || G % 128 || K < 1) return fail("tensor-core path supports res=skip=128, gate %% 128 == 0 (got %d,%d,%d)", R, S, G);
+        if (fl.tc_gate.empty()) { fl.tc_gate.resize(nb); fl.tc_resskip.resize(nb); }
+        // ---- gate: N = 2G in tiles of 256 = [128 filter | 128 gate] of the same 128 channels;
+        //      K chunks: taps 0..K-1 of h (R/64 chunks each), then the conditioning (ceil(CI/64) chunks)
+        const int hch = R / BK, cch = (CI + BK - 1) / BK;
+        const int nch = K * hch + cch, Kp = nch * BK, N = 2 * G;
+        std::vector<float> D((size_t)N * Kp, 0.f), Bb(N, 0.f);
+        for (int n = 0; n < N; ++n) {
+          const int nt = n / BN, r = n % BN;
+          const bool is_gate = r >= BN / 2;
+          const int j = nt * (BN / 2) + (r % (BN / 2));
+          const HostTensor& wk = is_gate ? wg : wf;
+          const HostTensor& wc = is_gate ? wgc : wfc;
+          Bb[n] = is_gate ? (bg->data[j] + bgc->data[j]) : (bf->data[j] + bfc->data[j]);
+          for (int tap = 0; tap < K; ++tap)
+            for (int cc = 0; cc < R; ++cc) D[(size_t)n * Kp + (size_t)tap * R + cc] = wk.data[((size_t)j * R + cc) * K + tap];
+          for (int cc = 0; cc < CI; ++cc) D[(size_t)n * Kp + (size_t)K * R + cc] = wc.data[(size_t)j * CI + cc];
+        }
+        TcPacked& tg = fl.tc_gate[i];
+        if (pack_tc(h, D, Bb, N, nch, &tg)) return 1;
+        tg.nseg = 2;
+        tg.seg[0] = {K, 0, 0, hch, BK / 16};
+        tg.seg[1] = {1, 1, 0, cch, ((CI - (cch - 1) * BK) + 15) / 16};
+        // ---- res/skip: N = 256 = [128 res | 128 skip], K = G
+        const int och = G / BK;
+        std::vector<float> D2((size_t)(R + S) * G, 0.f), Bb2(R + S, 0.f);
+        for (int m = 0; m < R; ++m) { Bb2[m] = br->data[m]; for (int cc = 0; cc < G; ++cc) D2[(size_t)m * G + cc] = wr.data[(size_t)m * G + cc]; }
+        for (int m = 0; m < S; ++m) { Bb2[R + m] = bs->data[m]; for (int cc = 0; cc < G; ++cc) D2[(size_t)(R + m) * G + cc] = ws.data[(size_t)m * G + cc]; }
+        TcPacked& tr = fl.tc_resskip[i];
+        if (pack_tc(h, D2, Bb2, R + S, och, &tr)) return 1;
+        tr.nseg = 1;
+        tr.seg[0] = {1, 1, 0, och, BK / 16};
+      }
     }
     if (pack_conv1d(h, fp + "final_conv.1.conv", S, S, 1, &fl.final1)) return 1;
     if (pack_small(h, fp + "final_conv.3.conv", 2, S, 1, &fl.final3)) return 1;
@@ -621,7 +743,8 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
   const int* lens_T = h->d_lens + (size_t)c.n_upsample * B;
   float *cmid, *cup, *hb, *ob, *sk, *y1, *za, *zb;
   if (ws_get(h, "c_up", (size_t)B * CI * T, &cup) || ws_get(h, "c_mid", (size_t)B * CI * (T / c.upsample_scales[c.n_upsample - 1] + 1), &cmid) ||
-      ws_get(h, "h", (size_t)B * R * T, &hb) || ws_get(h, "o", (size_t)B * G * T, &ob) ||
+      ws_get(h, "h", c.math == CUBE_MATH_TC_SPLIT16 ? 16 : (size_t)B * R * T, &hb) ||
+      ws_get(h, "o", c.math == CUBE_MATH_TC_SPLIT16 ? 16 : (size_t)B * G * T, &ob) ||
       ws_get(h, "skip", (size_t)B * S * T, &sk) || ws_get(h, "y1", (size_t)B * S * T, &y1) ||
       ws_get(h, "za", (size_t)B * T, &za) || ws_get(h, "zb", (size_t)B * T, &zb)) return 1;
   Launcher lx{h, st};
@@ -650,6 +773,36 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
   h->last_B = B; h->last_T = T;
   const float* zin = noise;
   const float rs = sqrtf(0.5f);
+  const bool use_tc = (c.math == CUBE_MATH_TC_SPLIT16);
+  __half *h16 = nullptr, *o16 = nullptr, *c16 = nullptr;
+  CUtensorMap tm_h, tm_o, tm_c;
+  if (use_tc) {
+    float *t1, *t2, *t3;
+    // fp16 (hi, lo) planes, channels-last: 2*2 bytes per element = the footprint of one fp32 tensor
+    if (ws_get(h, "h16", (size_t)B * T * R, &t1) || ws_get(h, "o16", (size_t)B * T * G, &t2) ||
+        ws_get(h, "c16", (size_t)B * T * CI, &t3)) return 1;
+    h16 = (__half*)t1; o16 = (__half*)t2; c16 = (__half*)t3;
+    if (make_tmap_hl16(&tm_h, h16, B, T, R) || make_tmap_hl16(&tm_o, o16, B, T, G) || make_tmap_hl16(&tm_c, c16, B, T, CI)) return 1;
+    static bool attr[64] = {false};
+    if (!attr[h->device & 63]) {
+      CU_TRY(cudaFuncSetAttribute(tc::tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+      attr[h->device & 63] = true;
+    }
+    lx.begin("to_hl16");
+    tc::to_hl16_kernel<<<dim3((T + 31) / 32, (CI + 31) / 32, B), 256, 0, st>>>(cup, c16, B, CI, T);
+    lx.check();
+    lx.end();
+  }
+  auto launch_tc = [&](const TcPacked& pk, tc::TcParams& tp) {
+    tp.Wimg = pk.Wimg; tp.inv_scale = pk.inv_scale; tp.bias = pk.bias;
+    tp.nseg = pk.nseg; tp.nchunks_total = pk.nchunks_total;
+    tp.B = B; tp.T = T; tp.n_tiles = pk.n_tiles; tp.t_tiles = (T + tc::BM - 1) / tc::BM;
+    tp.lens = lens_T;
+    const long long tiles = (long long)tp.n_tiles * tp.t_tiles * B;
+    const int grid = (int)std::min<long long>(tiles, h->sm_count);
+    tc::tc_conv_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(tp);
+    lx.check();
+  };
   for (int f = 0; f < c.n_flows; ++f) {
     cube_voc::Flow& fl = h->flows[f];
     const bool last_flow = (f == c.n_flows - 1);
@@ -660,13 +813,43 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
       p.nseg = 1;
       p.seg[0] = make_seg(zin, T, 1, T, c.front_kernel, 1, -(c.front_kernel - 1), PRE_NONE, 0.f, lens_T);
       p.Q = T; p.L_out = T; p.out_lens = lens_T; p.post = POST_RELU;
-      p.out = hb; p.out_bstride = (long long)R * T;
+      p.out = use_tc ? y1 : hb; p.out_bstride = (long long)R * T;
       lx.conv(p, B);
       lx.end();
+      if (use_tc) {
+        lx.begin("to_hl16");
+        tc::to_hl16_kernel<<<dim3((T + 31) / 32, (R + 31) / 32, B), 256, 0, st>>>(y1, h16, B, R, T);
+        lx.check();
+        lx.end();
+      }
     }
     const int nb = c.flow_blocks[f];
     for (int i = 0; i < nb; ++i) {
       const int d = dilation_of(c, i);
+      if (use_tc) {
+        {  // o = tanh(filter(h) + filter_c(c)) * sigmoid(gate(h) + gate_c(c))   [tcgen05]
+          lx.begin("gate");
+          tc::TcParams tp;
+          memset(&tp, 0, sizeof(tp));
+          tp.tmA[0] = tm_h; tp.tmA[1] = tm_c;
+          tp.seg[0] = fl.tc_gate[i].seg[0]; tp.seg[1] = fl.tc_gate[i].seg[1];
+          tp.seg[0].dil = d; tp.seg[0].off0 = -(K - 1) * d;
+          tp.epi = tc::TC_EPI_GATE; tp.out16 = o16; tp.outC = G;
+          launch_tc(fl.tc_gate[i], tp);
+          lx.end();
+        }
+        {  // h = (h + res(o)) * sqrt(.5);  skip += skip_conv(o)               [tcgen05]
+          lx.begin("resskip");
+          tc::TcParams tp;
+          memset(&tp, 0, sizeof(tp));
+          tp.tmA[0] = tm_o; tp.tmA[1] = tm_o;
+          tp.seg[0] = fl.tc_resskip[i].seg[0];
+          tp.epi = tc::TC_EPI_RESSKIP; tp.h16 = h16; tp.hC = R; tp.skip = sk; tp.skip_set = (i == 0); tp.scale = rs;
+          launch_tc(fl.tc_resskip[i], tp);
+          lx.end();
+        }
+        continue;
+      }
       {  // o = tanh(filter(h) + filter_c(c)) * sigmoid(gate(h) + gate_c(c))
         lx.begin("gate");
         ConvP p = make_conv(fl.gate[i]);

@@ -1,0 +1,415 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a: the dense layers of the ClariNet
+// residual stack (gated dilated causal conv + conditioning 1x1; res/skip 1x1) as
+//     D[M = 128 time steps, N = 256 output channels] += A[M, K] * B[N, K]^T
+// with error-compensated split-fp16 arithmetic: every fp32 value x is carried as (hi, lo) fp16 with
+// hi = fp16(x), lo = fp16(x - hi)  (22 significant bits), and the product is accumulated in fp32 as
+//     a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi          (3 tcgen05.mma per K-step, |err| ~ 2^-22)
+// which keeps the waveform within the 1e-3 budget where single-pass TF32/BF16/FP16 does not
+// (SURVEY hard-part 2).
+//
+// Data layout: activations are CHANNELS-LAST fp16 planes [2(hi,lo)][B][T][C]; a K-major A tile
+// (128 time rows x 64 channels = 128 B per row) is then ONE TMA box, the conv taps are the same box
+// at row offset -tap*dilation, and the causal / "same" zero padding is TMA's out-of-bounds fill.
+// Weights are pre-split, pre-scaled (power-of-two per output row, undone in the epilogue) and stored
+// as ready-made 128B-swizzled smem images, fetched with 1-D bulk copies (no tensor map).
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 =
+// epilogue (TMEM -> registers -> global).  Persistent CTAs, 2-stage smem ring of 96 KB stages,
+// double-buffered 2 x 256-column fp32 accumulators in TMEM.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cube {
+namespace tc {
+
+constexpr int BM = 128;          // time steps per tile (UMMA M)
+constexpr int BN = 256;          // output channels per tile (UMMA N)
+constexpr int BK = 64;           // channels per K chunk = one 128-byte swizzle span of fp16
+constexpr int STAGES = 2;
+constexpr int A_TILE_BYTES = BM * BK * 2;        // 16 KB per plane
+constexpr int B_TILE_BYTES = BN * BK * 2;        // 32 KB per plane
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 96 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 192;
+
+enum { TC_EPI_GATE = 0, TC_EPI_RESSKIP = 1 };
+
+struct TcSeg {
+  int taps, dil, off0;   // source row of output row t, tap j: t + off0 + j*dil
+  int nchunks;           // K chunks (of 64 channels) per tap
+  int last_ksteps;       // K steps (of 16 channels) that hold real data in the last chunk (1..4)
+};
+
+struct TcParams {
+  CUtensorMap tmA[2];       // per segment: fp16 [2B][T][C] channels-last, box {64, 128, 1}, SWIZZLE_128B
+  const __half* Wimg;       // [n_tiles][nchunks_total][2 planes][BN*BK] swizzled images
+  const float* inv_scale;   // [N] per-output-row power-of-two de-scale
+  const float* bias;        // [N]
+  TcSeg seg[2];
+  int nseg, nchunks_total;
+  int B, T, n_tiles, t_tiles;
+  const int* lens;          // [B] valid length (rows >= len are written as 0) or null
+  int epi;
+  // TC_EPI_GATE: o = tanh(f)*sigmoid(g) -> fp16 planes [2][B][T][outC], tile covers outC/n_tiles channels
+  __half* out16; int outC;
+  // TC_EPI_RESSKIP: cols [0,128): h = (h + v)*scale in place (fp16 planes [2][B][T][hC]);
+  //                 cols [128,256): skip[b][c][t] (=|+=) v   (fp32 channel-first)
+  __half* h16; int hC;
+  float* skip; int skip_set;
+  float scale;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate, single CTA
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all MMAs issued so far by this thread -> one arrival on the mbarrier
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile (rows of 128 B, 8-row groups 1024 B apart), sm_100 descriptor
+// (cute/arch/mma_sm100_desc.hpp: start>>4 [0,14), LBO [16,30), SBO [32,46), version=1 [46,48),
+//  layout SWIZZLE_128B=2 [61,64)).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;            // LBO (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;  // SBO = 1024 B between 8-row groups
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ __half f2h_sat(float x) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return __ushort_as_half(r);
+}
+__device__ __forceinline__ void split16(float x, __half& hi, __half& lo) {
+  hi = f2h_sat(x);
+  lo = f2h_sat(x - __half2float(hi));
+}
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.n_tiles * p.t_tiles * p.B;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmA[0]);
+    if (p.nseg > 1) prefetch_tmap(&p.tmA[1]);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int rest = tile / p.n_tiles;
+        const int tt = rest % p.t_tiles, b = rest / p.t_tiles;
+        const int t0 = tt * BM;
+        const __half* wt = p.Wimg + (size_t)nt * p.nchunks_total * 2 * (BN * BK);
+        int chunk = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const TcSeg sg = p.seg[s];
+          for (int tap = 0; tap < sg.taps; ++tap) {
+            const int row = t0 + sg.off0 + tap * sg.dil;
+            for (int cc = 0; cc < sg.nchunks; ++cc, ++chunk, ++it) {
+              const int st = it % STAGES;
+              const uint32_t par = (it / STAGES) & 1;
+              mbar_wait(&empty[st], par ^ 1);
+              uint8_t* sb = smem + st * STAGE_BYTES;
+              mbar_expect_tx(&full[st], STAGE_BYTES);
+              tma_load_3d(sb, &p.tmA[s], &full[st], cc * BK, row, b);
+              tma_load_3d(sb + A_TILE_BYTES, &p.tmA[s], &full[st], cc * BK, row, p.B + b);
+              const __half* wc = wt + (size_t)chunk * 2 * (BN * BK);
+              bulk_load(sb + 2 * A_TILE_BYTES, wc, B_TILE_BYTES, &full[st]);
+              bulk_load(sb + 2 * A_TILE_BYTES + B_TILE_BYTES, wc + BN * BK, B_TILE_BYTES, &full[st]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc();
+      uint32_t it = 0, titer = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
+        const uint32_t acc = titer & 1, aph = (titer >> 1) & 1;
+        mbar_wait(&tempty[acc], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const TcSeg sg = p.seg[s];
+          for (int tap = 0; tap < sg.taps; ++tap) {
+            for (int cc = 0; cc < sg.nchunks; ++cc, ++it) {
+              const int st = it % STAGES;
+              const uint32_t par = (it / STAGES) & 1;
+              mbar_wait(&full[st], par);
+              tc_fence_after();
+              const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES);
+              const uint32_t a_lo = a_hi + A_TILE_BYTES;
+              const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
+              const uint32_t b_lo = b_hi + B_TILE_BYTES;
+              const int ksteps = (cc == sg.nchunks - 1) ? sg.last_ksteps : (BK / 16);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t ko = ks * 32;  // 16 fp16 = 32 bytes along K inside the swizzle span
+                umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
+                accumulate = 1;
+                umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+                umma_f16(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+              }
+              umma_commit(&empty[st]);   // frees the smem stage when these MMAs have read it
+            }
+          }
+        }
+        umma_commit(&tfull[acc]);        // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 2..5) ===========================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;          // tile row = time step within the tile
+    uint32_t titer = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
+      const int nt = tile % p.n_tiles;
+      const int rest = tile / p.n_tiles;
+      const int tt = rest % p.t_tiles, b = rest / p.t_tiles;
+      const int t = tt * BM + row;
+      const uint32_t acc = titer & 1, aph = (titer >> 1) & 1;
+      mbar_wait(&tfull[acc], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      const int len = p.lens ? min(p.lens[b], p.T) : p.T;
+      const bool in_range = t < p.T;
+      const bool valid = t < len;
+      const int ncol0 = nt * BN;
+      if (p.epi == TC_EPI_GATE) {
+        // cols [0,128) filter, [128,256) gate of output channels nt*128 + c
+        const size_t plane = (size_t)p.B * p.T * p.outC;
+        __half* orow = p.out16 + ((size_t)b * p.T + t) * p.outC + nt * (BN / 2);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+          uint32_t f[32], g[32];
+          tmem_ld32(taddr + c0, f);
+          tmem_ld32(taddr + BN / 2 + c0, g);
+          tmem_ld_wait();
+          if (in_range) {
+            __align__(16) __half hi[32];
+            __align__(16) __half lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int cf = ncol0 + c0 + j, cg = ncol0 + BN / 2 + c0 + j;
+              const float fv = __uint_as_float(f[j]) * __ldg(p.inv_scale + cf) + __ldg(p.bias + cf);
+              const float gv = __uint_as_float(g[j]) * __ldg(p.inv_scale + cg) + __ldg(p.bias + cg);
+              const float o = valid ? tanhf(fv) * sigmoidf_acc(gv) : 0.f;
+              split16(o, hi[j], lo[j]);
+            }
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              reinterpret_cast<uint4*>(orow + c0)[v] = reinterpret_cast<const uint4*>(hi)[v];
+              reinterpret_cast<uint4*>(orow + plane + c0)[v] = reinterpret_cast<const uint4*>(lo)[v];
+            }
+          }
+        }
+      } else {
+        // cols [0,128): residual stream (in place, fp16 planes); cols [128,256): skip (fp32 [B][128][T])
+        const size_t plane = (size_t)p.B * p.T * p.hC;
+        __half* hrow = p.h16 + ((size_t)b * p.T + t) * p.hC;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          tmem_ld_wait();
+          if (in_range) {
+            __align__(16) __half hi[32];
+            __align__(16) __half lo[32];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              reinterpret_cast<uint4*>(hi)[v] = reinterpret_cast<const uint4*>(hrow + c0)[v];
+              reinterpret_cast<uint4*>(lo)[v] = reinterpret_cast<const uint4*>(hrow + plane + c0)[v];
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int c = c0 + j;
+              const float v = __uint_as_float(r[j]) * __ldg(p.inv_scale + c) + __ldg(p.bias + c);
+              const float hold = __half2float(hi[j]) + __half2float(lo[j]);
+              const float hn = valid ? (hold + v) * p.scale : 0.f;
+              split16(hn, hi[j], lo[j]);
+            }
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              reinterpret_cast<uint4*>(hrow + c0)[v] = reinterpret_cast<const uint4*>(hi)[v];
+              reinterpret_cast<uint4*>(hrow + plane + c0)[v] = reinterpret_cast<const uint4*>(lo)[v];
+            }
+          }
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + BN / 2 + c0, r);
+          tmem_ld_wait();
+          if (in_range) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int c = BN / 2 + c0 + j;
+              const float v = __uint_as_float(r[j]) * __ldg(p.inv_scale + c) + __ldg(p.bias + c);
+              float* sp = p.skip + ((size_t)b * (BN / 2) + (c0 + j)) * p.T + t;   // lanes -> consecutive t: coalesced
+              const float y = p.skip_set ? v : (*sp + v);
+              *sp = valid ? y : 0.f;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 [B][C][T] (channel-first) -> fp16 hi/lo planes [2][B][T][C] (channels-last); tiled transpose
+// through shared memory so both sides are coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) to_hl16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int B, int C, int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    tile[i][tx] = (c < C && t < T) ? src[((size_t)b * C + c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  const size_t plane = (size_t)B * T * C;
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    if (t < T && c < C) {
+      __half hi, lo;
+      split16(tile[tx][i], hi, lo);
+      const size_t o = ((size_t)b * T + t) * C + c;
+      dst[o] = hi;
+      dst[plane + o] = lo;
+    }
+  }
+}
+
+}  // namespace tc
+}  // namespace cube
