@@ -13,8 +13,8 @@
 // Weights are pre-split, pre-scaled (power-of-two per output row, undone in the epilogue) and stored
 // as ready-made 128B-swizzled smem images, fetched with 1-D bulk copies (no tensor map).
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 =
-// epilogue (TMEM -> registers -> global).  Persistent CTAs, 2-stage smem ring of 96 KB stages,
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 =
+// epilogue (TMEM -> registers -> global; two warps per TMEM lane quarter, each half the columns).  Persistent CTAs, 2-stage smem ring of 96 KB stages,
 // double-buffered 2 x 256-column fp32 accumulators in TMEM.
 #pragma once
 #include <cuda.h>
@@ -32,8 +32,9 @@ constexpr int STAGES = 2;
 constexpr int A_TILE_BYTES = BM * BK * 2;        // 16 KB per plane
 constexpr int B_TILE_BYTES = BN * BK * 2;        // 32 KB per plane
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 96 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BN * 8 /*scale,bias*/;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
 
 enum { TC_EPI_GATE = 0, TC_EPI_RESSKIP = 1 };
 
@@ -177,7 +178,9 @@ __device__ __forceinline__ void split16(float x, __half& hi, __half& lo) {
   hi = f2h_sat(x);
   lo = f2h_sat(x - __half2float(hi));
 }
-__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
+// gate non-linearities on the SFU: ex2.approx + rcp.approx, abs error ~1e-6 (budget 1e-3)
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 // ------------------------------------------------------------------------------------------------
 // the kernel
@@ -191,6 +194,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
   uint64_t* tfull = bars + 2 * STAGES;   // [2]
   uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float2* s_sb = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 256);   // [BN] (inv_scale, bias) of this tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.n_tiles * p.t_tiles * p.B;
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
     prefetch_tmap(&p.tmA[0]);
     if (p.nseg > 1) prefetch_tmap(&p.tmA[1]);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], NUM_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
@@ -278,9 +282,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
       }
     }
   } else {
-    // =========================== epilogue (warps 2..5) ===========================
+    // =========================== epilogue (warps 2..9) ===========================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // which half of the tile's columns this warp owns
     const int row = q * 32 + lane;          // tile row = time step within the tile
+    const int etid = threadIdx.x - 64;      // 0..255
     uint32_t titer = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
       const int nt = tile % p.n_tiles;
@@ -288,19 +294,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
       const int tt = rest % p.t_tiles, b = rest / p.t_tiles;
       const int t = tt * BM + row;
       const uint32_t acc = titer & 1, aph = (titer >> 1) & 1;
+      // per-column (de-scale, bias) of this tile -> smem (one column per epilogue thread)
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // previous tile's readers are done
+      s_sb[etid] = make_float2(__ldg(p.inv_scale + nt * BN + etid), __ldg(p.bias + nt * BN + etid));
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
       const int len = p.lens ? min(p.lens[b], p.T) : p.T;
       const bool in_range = t < p.T;
       const bool valid = t < len;
-      const int ncol0 = nt * BN;
       if (p.epi == TC_EPI_GATE) {
-        // cols [0,128) filter, [128,256) gate of output channels nt*128 + c
+        // cols [0,128) filter, [128,256) gate of output channels nt*128 + c; this warp: c in [64*half, +64)
         const size_t plane = (size_t)p.B * p.T * p.outC;
         __half* orow = p.out16 + ((size_t)b * p.T + t) * p.outC + nt * (BN / 2);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+        for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
           uint32_t f[32], g[32];
           tmem_ld32(taddr + c0, f);
           tmem_ld32(taddr + BN / 2 + c0, g);
@@ -310,10 +319,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
             __align__(16) __half lo[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const int cf = ncol0 + c0 + j, cg = ncol0 + BN / 2 + c0 + j;
-              const float fv = __uint_as_float(f[j]) * __ldg(p.inv_scale + cf) + __ldg(p.bias + cf);
-              const float gv = __uint_as_float(g[j]) * __ldg(p.inv_scale + cg) + __ldg(p.bias + cg);
-              const float o = valid ? tanhf(fv) * sigmoidf_acc(gv) : 0.f;
+              const float2 sf = s_sb[c0 + j], sg = s_sb[BN / 2 + c0 + j];
+              const float fv = fmaf(__uint_as_float(f[j]), sf.x, sf.y);
+              const float gv = fmaf(__uint_as_float(g[j]), sg.x, sg.y);
+              const float o = valid ? tanh_fast(fv) * sigmoid_fast(gv) : 0.f;
               split16(o, hi[j], lo[j]);
             }
 #pragma unroll
@@ -323,27 +332,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
             }
           }
         }
-      } else {
-        // cols [0,128): residual stream (in place, fp16 planes); cols [128,256): skip (fp32 [B][128][T])
+      } else if (half == 0) {
+        // cols [0,128): residual stream, updated in place (fp16 planes)
         const size_t plane = (size_t)p.B * p.T * p.hC;
         __half* hrow = p.h16 + ((size_t)b * p.T + t) * p.hC;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN / 2; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(taddr + c0, r);
-          tmem_ld_wait();
+          __align__(16) __half hi[32];
+          __align__(16) __half lo[32];
           if (in_range) {
-            __align__(16) __half hi[32];
-            __align__(16) __half lo[32];
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
               reinterpret_cast<uint4*>(hi)[v] = reinterpret_cast<const uint4*>(hrow + c0)[v];
               reinterpret_cast<uint4*>(lo)[v] = reinterpret_cast<const uint4*>(hrow + plane + c0)[v];
             }
+          }
+          tmem_ld_wait();
+          if (in_range) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const int c = c0 + j;
-              const float v = __uint_as_float(r[j]) * __ldg(p.inv_scale + c) + __ldg(p.bias + c);
+              const float2 sb = s_sb[c0 + j];
+              const float v = fmaf(__uint_as_float(r[j]), sb.x, sb.y);
               const float hold = __half2float(hi[j]) + __half2float(lo[j]);
               const float hn = valid ? (hold + v) * p.scale : 0.f;
               split16(hn, hi[j], lo[j]);
@@ -355,19 +366,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
             }
           }
         }
+      } else {
+        // cols [128,256): skip accumulator, fp32 [B][128][T]; lanes -> consecutive t: coalesced.
+        // All 32 loads are issued before the first use (the compiler may not hoist them over the
+        // stores of the previous column by itself).
+        float* sp0 = p.skip + (size_t)b * (BN / 2) * p.T + t;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN / 2; c0 += 32) {
           uint32_t r[32];
+          float old[32];
           tmem_ld32(taddr + BN / 2 + c0, r);
+          if (in_range && !p.skip_set) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) old[j] = __ldcs(sp0 + (size_t)(c0 + j) * p.T);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) old[j] = 0.f;
+          }
           tmem_ld_wait();
           if (in_range) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const int c = BN / 2 + c0 + j;
-              const float v = __uint_as_float(r[j]) * __ldg(p.inv_scale + c) + __ldg(p.bias + c);
-              float* sp = p.skip + ((size_t)b * (BN / 2) + (c0 + j)) * p.T + t;   // lanes -> consecutive t: coalesced
-              const float y = p.skip_set ? v : (*sp + v);
-              *sp = valid ? y : 0.f;
+              const float2 sb = s_sb[BN / 2 + c0 + j];
+              const float y = old[j] + fmaf(__uint_as_float(r[j]), sb.x, sb.y);
+              __stcs(sp0 + (size_t)(c0 + j) * p.T, valid ? y : 0.f);
             }
           }
         }
