@@ -216,9 +216,9 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    math = {"auto": _lib.MATH_FP32_SIMT, "simt": _lib.MATH_FP32_SIMT, "tc": _lib.MATH_TC_SPLIT16}[args.math]
-    if args.math == "auto" and os.environ.get("CUBE_MATH", "") == "tc":
-        math = _lib.MATH_TC_SPLIT16
+    # auto: tensor cores (split-fp16 x3) for the student's residual stack; HiFi-GAN runs the fp32 path
+    math = {"auto": _lib.MATH_TC_SPLIT16 if arch == "student" else _lib.MATH_FP32_SIMT,
+            "simt": _lib.MATH_FP32_SIMT, "tc": _lib.MATH_TC_SPLIT16}[args.math]
     weights, wdesc = load_weights(arch)
     if arch == "student":
         voc = cube.ParallelWaveNetVocoder(weights[0], weights[1], math=math).to(dev)
@@ -303,7 +303,8 @@ def main():
         dom_ms = prof.get(dom, 0.0)
         flops_launch = GATE_FLOPS * samples_per_step
         ach = flops_launch * nlaunch / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else None
-        roof = {"kernel": "conv_tile_kernel (gated dilated conv + conditioning 1x1, EPI_GATE)" if math == 0 else "tc gate",
+        roof = {"kernel": "conv_tile_kernel<8,8,8,1> EPI_GATE (gated dilated conv k3 128->2x256 + conditioning 1x1 80->2x256, fp32 FFMA2)" if math == 0
+                else "tc::tc_conv_kernel TC_EPI_GATE (same layer on tcgen05: UMMA 128x256x16 f16, split-fp16 x3, TMA taps)",
                 "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                 "frac": (ach / pk["tf_sust"]) if ach else None, "traffic": None,
                 "launches_per_step": nlaunch, "avg_launch_ms": dom_ms / max(1, nlaunch),

@@ -105,6 +105,8 @@ struct cube_voc {
     PackedConv front, final1, final3;
     std::vector<PackedConv> gate, resskip;
     std::vector<TcPacked> tc_gate, tc_resskip;
+    TcPacked tc_final1;
+    float* w3 = nullptr;   // final_conv.3: [2][S] weights + [2] bias (fp32), for the fused FINAL epilogue
   };
   std::vector<Flow> flows;
   struct Up2 { float w[192]; float bias; int s; };
@@ -274,7 +276,7 @@ static int pack_tc(cube_voc* h, const std::vector<float>& dense, const std::vect
         const float w = dense[(size_t)n * Kp + ch * BK + kk] * sc;
         const __half hi = __float2half_rn(w);
         const __half lo = __float2half_rn(w - __half2float(hi));
-        const size_t off = (size_t)(r / 8) * 512 + (size_t)(r % 8) * 64 + (size_t)(((kk / 8) ^ (r % 8)) * 8) + (kk % 8);
+        const size_t off = (size_t)swz_off(r, kk);
         const size_t base = ((size_t)(nt * nchunks + ch) * 2) * (BN * BK);
         img[base + off] = hi;
         img[base + (size_t)BN * BK + off] = lo;
@@ -308,7 +310,8 @@ static int make_tmap_hl16(CUtensorMap* tm, const __half* base, int B, int T, int
   cuuint32_t box[3] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  tc::BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for [2*%d][%d][%d]", (int)r, B, T, C);
   return 0;
 }
@@ -552,6 +555,22 @@ static int finalize_student(cube_voc* h) {
     }
     if (pack_conv1d(h, fp + "final_conv.1.conv", S, S, 1, &fl.final1)) return 1;
     if (pack_small(h, fp + "final_conv.3.conv", 2, S, 1, &fl.final3)) return 1;
+    if (c.math == CUBE_MATH_TC_SPLIT16) {
+      using namespace tc;
+      HostTensor w1, w3; const HostTensor *b1, *b3;
+      if (get_weight(h, fp + "final_conv.1.conv", &w1) || get_bias(h, fp + "final_conv.1.conv", S, &b1)) return 1;
+      if (get_weight(h, fp + "final_conv.3.conv", &w3) || get_bias(h, fp + "final_conv.3.conv", 2, &b3)) return 1;
+      // final_conv.1 as a [256 x S] GEMM (rows >= S are zero padding of the 256-column tile)
+      std::vector<float> D((size_t)BN * S, 0.f), Bb(BN, 0.f);
+      for (int m = 0; m < S; ++m) { Bb[m] = b1->data[m]; for (int cc = 0; cc < S; ++cc) D[(size_t)m * S + cc] = w1.data[(size_t)m * S + cc]; }
+      if (pack_tc(h, D, Bb, BN, S / BK, &fl.tc_final1)) return 1;
+      fl.tc_final1.nseg = 1;
+      fl.tc_final1.seg[0] = {1, 1, 0, S / BK, BK / 16};
+      std::vector<float> W3(2 * S + 2);
+      for (int cc = 0; cc < S; ++cc) { W3[cc] = w3.data[cc]; W3[S + cc] = w3.data[S + cc]; }
+      W3[2 * S] = b3->data[0]; W3[2 * S + 1] = b3->data[1];
+      if (dev_upload(h, W3, &fl.w3)) return 1;
+    }
   }
   // UpsampleNet2 (teacher's upsample_conv.{0,2}): [1,1,3,2s]
   h->up2.resize(c.n_upsample);
@@ -774,10 +793,13 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
   const float* zin = noise;
   const float rs = sqrtf(0.5f);
   const bool use_tc = (c.math == CUBE_MATH_TC_SPLIT16);
-  __half *h16 = nullptr, *o16 = nullptr, *c16 = nullptr;
-  CUtensorMap tm_h, tm_o, tm_c;
+  __half *h16 = nullptr, *o16 = nullptr, *c16 = nullptr, *s16 = nullptr;
+  CUtensorMap tm_h, tm_o, tm_c, tm_s;
   if (use_tc) {
-    float *t1, *t2, *t3;
+    float *t1, *t2, *t3, *t4;
+    if (ws_get(h, "s16", (size_t)B * T * S, &t4)) return 1;
+    s16 = (__half*)t4;
+    if (make_tmap_hl16(&tm_s, s16, B, T, S)) return 1;
     // fp16 (hi, lo) planes, channels-last: 2*2 bytes per element = the footprint of one fp32 tensor
     if (ws_get(h, "h16", (size_t)B * T * R, &t1) || ws_get(h, "o16", (size_t)B * T * G, &t2) ||
         ws_get(h, "c16", (size_t)B * T * CI, &t3)) return 1;
@@ -845,6 +867,7 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
           tp.tmA[0] = tm_o; tp.tmA[1] = tm_o;
           tp.seg[0] = fl.tc_resskip[i].seg[0];
           tp.epi = tc::TC_EPI_RESSKIP; tp.h16 = h16; tp.hC = R; tp.skip = sk; tp.skip_set = (i == 0); tp.scale = rs;
+          tp.skip16 = (i == nb - 1) ? s16 : nullptr;   // last block: relu(skip) straight into the final GEMM's A planes
           launch_tc(fl.tc_resskip[i], tp);
           lx.end();
         }
@@ -873,6 +896,18 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
         lx.conv(p, B);
         lx.end();
       }
+    }
+    if (use_tc) {  // final_conv.1 on tensor cores with relu -> final_conv.3 -> IAF affine fused in the epilogue
+      lx.begin("final_iaf_tc");
+      tc::TcParams tp;
+      memset(&tp, 0, sizeof(tp));
+      tp.tmA[0] = tm_s; tp.tmA[1] = tm_s;
+      tp.seg[0] = fl.tc_final1.seg[0];
+      tp.epi = tc::TC_EPI_FINAL; tp.w3 = fl.w3; tp.z_in = zin; tp.z_out = zout;
+      launch_tc(fl.tc_final1, tp);
+      lx.end();
+      zin = zout;
+      continue;
     }
     {  // y1 = conv1x1(relu(skip))
       lx.begin("final1");

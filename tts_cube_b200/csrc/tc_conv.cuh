@@ -13,8 +13,8 @@
 // Weights are pre-split, pre-scaled (power-of-two per output row, undone in the epilogue) and stored
 // as ready-made 128B-swizzled smem images, fetched with 1-D bulk copies (no tensor map).
 //
-// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 =
-// epilogue (TMEM -> registers -> global; two warps per TMEM lane quarter, each half the columns).  Persistent CTAs, 2-stage smem ring of 96 KB stages,
+// Roles (576 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-17 =
+// epilogue (TMEM -> registers -> global; four warps per TMEM lane quarter, a quarter of the columns each).  Persistent CTAs, 2-stage smem ring of 96 KB stages,
 // double-buffered 2 x 256-column fp32 accumulators in TMEM.
 #pragma once
 #include <cuda.h>
@@ -27,21 +27,33 @@ namespace tc {
 
 constexpr int BM = 128;          // time steps per tile (UMMA M)
 constexpr int BN = 256;          // output channels per tile (UMMA N)
-constexpr int BK = 64;           // channels per K chunk = one 128-byte swizzle span of fp16
-constexpr int STAGES = 2;
-constexpr int A_TILE_BYTES = BM * BK * 2;        // 16 KB per plane
-constexpr int B_TILE_BYTES = BN * BK * 2;        // 32 KB per plane
-constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 96 KB
+#ifndef CUBE_TC_BK
+#define CUBE_TC_BK 32
+#endif
+constexpr int BK = CUBE_TC_BK;   // channels per K chunk = one swizzle span of fp16 (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B)
+constexpr int STAGES = (BK == 64) ? 2 : 4;       // 2 x 96 KB or 4 x 48 KB: same smem, deeper prefetch with BK=32
+constexpr int ROW_BYTES = BK * 2;                // bytes per tile row = swizzle span
+constexpr int SBO_BYTES = 8 * ROW_BYTES;         // 8-row core-matrix group stride
+static_assert(BK == 64 || BK == 32, "BK must be 64 (SW128) or 32 (SW64)");
+constexpr int A_TILE_BYTES = BM * BK * 2;        // 16 / 8 KB per plane
+constexpr int B_TILE_BYTES = BN * BK * 2;        // 32 / 16 KB per plane
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 96 / 48 KB
+
+// position (in fp16 elements) of element (row r, k) inside a swizzled [rows][BK] K-major tile image
+__host__ __device__ constexpr int swz_off(int r, int k) {
+  return (BK == 64) ? (r / 8) * 512 + (r % 8) * 64 + (((k / 8) ^ (r % 8)) * 8) + (k % 8)
+                    : r * 32 + (((k / 8) ^ ((r >> 1) & 3)) * 8) + (k % 8);
+}
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BN * 8 /*scale,bias*/;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
 
-enum { TC_EPI_GATE = 0, TC_EPI_RESSKIP = 1 };
+enum { TC_EPI_GATE = 0, TC_EPI_RESSKIP = 1, TC_EPI_FINAL = 2 };
 
 struct TcSeg {
   int taps, dil, off0;   // source row of output row t, tap j: t + off0 + j*dil
-  int nchunks;           // K chunks (of 64 channels) per tap
-  int last_ksteps;       // K steps (of 16 channels) that hold real data in the last chunk (1..4)
+  int nchunks;           // K chunks (of BK channels) per tap
+  int last_ksteps;       // K steps (of 16 channels) that hold real data in the last chunk (1..BK/16)
 };
 
 struct TcParams {
@@ -61,6 +73,12 @@ struct TcParams {
   __half* h16; int hC;
   float* skip; int skip_set;
   float scale;
+  __half* skip16;           // RESSKIP, last block of a flow: relu(skip total) as fp16 planes [2][B][T][128]
+                            // (the A operand of the flow's final 1x1) instead of the fp32 store
+  // TC_EPI_FINAL: cols [0,128) = final_conv.1 output y1; fused relu -> final_conv.3 (128->2) -> IAF:
+  //   z_out[t+1] = z_in[t+1]*exp(logs[t]) + mu[t], z_out[0] = 0
+  const float* w3;          // [2][128] + bias [2]
+  const float* z_in; float* z_out;   // [B][T]
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -151,16 +169,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, 128B-swizzled operand tile (rows of 128 B, 8-row groups 1024 B apart), sm_100 descriptor
+// K-major, swizzled operand tile (rows of ROW_BYTES, 8-row groups SBO_BYTES apart), sm_100 descriptor
 // (cute/arch/mma_sm100_desc.hpp: start>>4 [0,14), LBO [16,30), SBO [32,46), version=1 [46,48),
-//  layout SWIZZLE_128B=2 [61,64)).
+//  layout [61,64): SWIZZLE_128B=2, SWIZZLE_64B=4).
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;            // LBO (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;  // SBO = 1024 B between 8-row groups
-  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  d |= (uint64_t)1 << 16;                 // LBO (unused for swizzled K-major)
+  d |= (uint64_t)(SBO_BYTES >> 4) << 32;  // SBO between 8-row groups
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)(BK == 64 ? 2 : 4) << 61;
   return d;
 }
 
@@ -178,6 +196,37 @@ __device__ __forceinline__ void split16(float x, __half& hi, __half& lo) {
   hi = f2h_sat(x);
   lo = f2h_sat(x - __half2float(hi));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// (x0, x1) -> packed fp16 pair {x1 : x0} with saturation, and the residual pair
+__device__ __forceinline__ uint32_t pack_h2_sat(float x0, float x1) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+  return r;
+}
+__device__ __forceinline__ void split16x2(float x0, float x1, uint32_t& hi2, uint32_t& lo2) {
+  hi2 = pack_h2_sat(x0, x1);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+  lo2 = pack_h2_sat(x0 - hf.x, x1 - hf.y);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+
 // gate non-linearities on the SFU: ex2.approx + rcp.approx, abs error ~1e-6 (budget 1e-3)
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
@@ -282,11 +331,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
       }
     }
   } else {
-    // =========================== epilogue (warps 2..9) ===========================
+    // =========================== epilogue (warps 2..17) ===========================
+    constexpr float LOG2E = 1.4426950408889634f;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;       // which half of the tile's columns this warp owns
+    const int sub = (warp - 2) >> 2;        // 0..3: which quarter of the tile's work this warp owns
     const int row = q * 32 + lane;          // tile row = time step within the tile
-    const int etid = threadIdx.x - 64;      // 0..255
+    const int etid = threadIdx.x - 64;      // 0..511
     uint32_t titer = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
       const int nt = tile % p.n_tiles;
@@ -294,10 +344,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
       const int tt = rest % p.t_tiles, b = rest / p.t_tiles;
       const int t = tt * BM + row;
       const uint32_t acc = titer & 1, aph = (titer >> 1) & 1;
-      // per-column (de-scale, bias) of this tile -> smem (one column per epilogue thread)
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // previous tile's readers are done
-      s_sb[etid] = make_float2(__ldg(p.inv_scale + nt * BN + etid), __ldg(p.bias + nt * BN + etid));
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // per-column (de-scale, bias) of this tile -> smem.  For the gate the exp2 pre-factors are
+      // folded in: filter columns carry 2*log2(e) (-> 2^a = e^{2f}), gate columns -log2(e) (-> e^{-g}).
+      asm volatile("bar.sync 1, 512;" ::: "memory");   // previous tile's readers are done
+      if (etid < BN) {
+        float sc = __ldg(p.inv_scale + nt * BN + etid), bi = __ldg(p.bias + nt * BN + etid);
+        if (p.epi == TC_EPI_GATE) {
+          const float k = etid < BN / 2 ? 2.f * LOG2E : -LOG2E;
+          sc *= k; bi *= k;
+        }
+        s_sb[etid] = make_float2(sc, bi);
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
@@ -305,91 +363,142 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
       const bool in_range = t < p.T;
       const bool valid = t < len;
       if (p.epi == TC_EPI_GATE) {
-        // cols [0,128) filter, [128,256) gate of output channels nt*128 + c; this warp: c in [64*half, +64)
+        // cols [0,128) filter, [128,256) gate of output channels nt*128 + c; this warp: c in [32*sub, +32)
+        //   o = tanh(f)*sigmoid(g) = (E1 - 1) / ((E1 + 1)(1 + E2)),  E1 = e^{2f}, E2 = e^{-g}: 2 ex2 + 1 rcp
         const size_t plane = (size_t)p.B * p.T * p.outC;
         __half* orow = p.out16 + ((size_t)b * p.T + t) * p.outC + nt * (BN / 2);
-#pragma unroll 1
-        for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
-          uint32_t f[32], g[32];
-          tmem_ld32(taddr + c0, f);
-          tmem_ld32(taddr + BN / 2 + c0, g);
+#pragma unroll
+        for (int cc = sub * 32; cc < sub * 32 + 32; cc += 16) {
+          uint32_t f[16], g[16];
+          tmem_ld16(taddr + cc, f);
+          tmem_ld16(taddr + BN / 2 + cc, g);
           tmem_ld_wait();
-          if (in_range) {
-            __align__(16) __half hi[32];
-            __align__(16) __half lo[32];
+          uint32_t hi2[8], lo2[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float2 sf = s_sb[c0 + j], sg = s_sb[BN / 2 + c0 + j];
-              const float fv = fmaf(__uint_as_float(f[j]), sf.x, sf.y);
-              const float gv = fmaf(__uint_as_float(g[j]), sg.x, sg.y);
-              const float o = valid ? tanh_fast(fv) * sigmoid_fast(gv) : 0.f;
-              split16(o, hi[j], lo[j]);
+          for (int j = 0; j < 16; j += 2) {
+            float o[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float2 sf = s_sb[cc + j + u], sg = s_sb[BN / 2 + cc + j + u];
+              const float a = fminf(fmaxf(fmaf(__uint_as_float(f[j + u]), sf.x, sf.y), -40.f), 40.f);
+              const float e = fminf(fmaf(__uint_as_float(g[j + u]), sg.x, sg.y), 60.f);
+              const float E1 = ex2_fast(a), E2 = ex2_fast(e);
+              o[u] = valid ? (E1 - 1.f) * rcp_fast((E1 + 1.f) * (1.f + E2)) : 0.f;
             }
+            split16x2(o[0], o[1], hi2[j >> 1], lo2[j >> 1]);
+          }
+          if (in_range) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              reinterpret_cast<uint4*>(orow + c0)[v] = reinterpret_cast<const uint4*>(hi)[v];
-              reinterpret_cast<uint4*>(orow + plane + c0)[v] = reinterpret_cast<const uint4*>(lo)[v];
+            for (int v = 0; v < 2; ++v) {
+              reinterpret_cast<uint4*>(orow + cc)[v] = make_uint4(hi2[4 * v], hi2[4 * v + 1], hi2[4 * v + 2], hi2[4 * v + 3]);
+              reinterpret_cast<uint4*>(orow + plane + cc)[v] = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
             }
           }
         }
-      } else if (half == 0) {
-        // cols [0,128): residual stream, updated in place (fp16 planes)
-        const size_t plane = (size_t)p.B * p.T * p.hC;
-        __half* hrow = p.h16 + ((size_t)b * p.T + t) * p.hC;
+      } else if (p.epi == TC_EPI_FINAL) {
+        if (sub == 0) {
+          // y1 = cols [0,128); (mu, logs) = W3 . relu(y1) + b3; IAF affine on sample t+1
+          float mu = __ldg(p.w3 + 2 * (BN / 2)), logs = __ldg(p.w3 + 2 * (BN / 2) + 1);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN / 2; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c0, r);
-          __align__(16) __half hi[32];
-          __align__(16) __half lo[32];
-          if (in_range) {
+          for (int c0 = 0; c0 < BN / 2; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              reinterpret_cast<uint4*>(hi)[v] = reinterpret_cast<const uint4*>(hrow + c0)[v];
-              reinterpret_cast<uint4*>(lo)[v] = reinterpret_cast<const uint4*>(hrow + plane + c0)[v];
+            for (int j = 0; j < 16; ++j) {
+              const float2 sb = s_sb[c0 + j];
+              const float y = fmaxf(fmaf(__uint_as_float(r[j]), sb.x, sb.y), 0.f);
+              mu = fmaf(y, __ldg(p.w3 + c0 + j), mu);
+              logs = fmaf(y, __ldg(p.w3 + (BN / 2) + c0 + j), logs);
             }
           }
-          tmem_ld_wait();
+          if (in_range) {
+            float* zo = p.z_out + (size_t)b * p.T;
+            if (t == 0) zo[0] = 0.f;
+            if (t + 1 < p.T) zo[t + 1] = (t + 1 < len) ? fmaf(p.z_in[(size_t)b * p.T + t + 1], expf(logs), mu) : 0.f;
+          }
+        }
+      } else if (sub < 2) {
+        // cols [0,128): residual stream, updated in place (fp16 planes); this warp: c in [64*sub, +64)
+        const size_t plane = (size_t)p.B * p.T * p.hC;
+        __half* hrow = p.h16 + ((size_t)b * p.T + t) * p.hC;
+#pragma unroll
+        for (int cc = sub * 64; cc < sub * 64 + 64; cc += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + cc, r);
+          uint4 hv[2], lv[2];
           if (in_range) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float2 sb = s_sb[c0 + j];
-              const float v = fmaf(__uint_as_float(r[j]), sb.x, sb.y);
-              const float hold = __half2float(hi[j]) + __half2float(lo[j]);
-              const float hn = valid ? (hold + v) * p.scale : 0.f;
-              split16(hn, hi[j], lo[j]);
+            for (int v = 0; v < 2; ++v) {
+              hv[v] = reinterpret_cast<const uint4*>(hrow + cc)[v];
+              lv[v] = reinterpret_cast<const uint4*>(hrow + plane + cc)[v];
             }
+          } else {
+            hv[0] = hv[1] = lv[0] = lv[1] = make_uint4(0, 0, 0, 0);
+          }
+          tmem_ld_wait();
+          const uint32_t* hp = reinterpret_cast<const uint32_t*>(hv);
+          const uint32_t* lp = reinterpret_cast<const uint32_t*>(lv);
+          uint32_t hi2[8], lo2[8];
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              reinterpret_cast<uint4*>(hrow + c0)[v] = reinterpret_cast<const uint4*>(hi)[v];
-              reinterpret_cast<uint4*>(hrow + plane + c0)[v] = reinterpret_cast<const uint4*>(lo)[v];
+          for (int j = 0; j < 16; j += 2) {
+            const float2 s0 = s_sb[cc + j], s1 = s_sb[cc + j + 1];
+            const float2 oh = unpack_h2(hp[j >> 1]), ol = unpack_h2(lp[j >> 1]);
+            const float v0 = fmaf(__uint_as_float(r[j]), s0.x, s0.y), v1 = fmaf(__uint_as_float(r[j + 1]), s1.x, s1.y);
+            const float n0 = valid ? ((oh.x + ol.x) + v0) * p.scale : 0.f;
+            const float n1 = valid ? ((oh.y + ol.y) + v1) * p.scale : 0.f;
+            split16x2(n0, n1, hi2[j >> 1], lo2[j >> 1]);
+          }
+          if (in_range) {
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              reinterpret_cast<uint4*>(hrow + cc)[v] = make_uint4(hi2[4 * v], hi2[4 * v + 1], hi2[4 * v + 2], hi2[4 * v + 3]);
+              reinterpret_cast<uint4*>(hrow + plane + cc)[v] = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
             }
           }
         }
       } else {
         // cols [128,256): skip accumulator, fp32 [B][128][T]; lanes -> consecutive t: coalesced.
-        // All 32 loads are issued before the first use (the compiler may not hoist them over the
-        // stores of the previous column by itself).
+        // this warp: skip channels [64*(sub-2), +64).  All loads of a chunk are issued before the
+        // first use (the compiler may not hoist them over the previous column's store by itself).
         float* sp0 = p.skip + (size_t)b * (BN / 2) * p.T + t;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN / 2; c0 += 32) {
-          uint32_t r[32];
-          float old[32];
-          tmem_ld32(taddr + BN / 2 + c0, r);
+#pragma unroll
+        for (int cc = (sub - 2) * 64; cc < (sub - 2) * 64 + 64; cc += 16) {
+          uint32_t r[16];
+          float old[16];
+          tmem_ld16(taddr + BN / 2 + cc, r);
           if (in_range && !p.skip_set) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) old[j] = __ldcs(sp0 + (size_t)(c0 + j) * p.T);
+            for (int j = 0; j < 16; ++j) old[j] = __ldcs(sp0 + (size_t)(cc + j) * p.T);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) old[j] = 0.f;
+            for (int j = 0; j < 16; ++j) old[j] = 0.f;
           }
           tmem_ld_wait();
-          if (in_range) {
+          if (p.skip16) {
+            uint32_t hi2[8], lo2[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float2 sb = s_sb[BN / 2 + c0 + j];
+            for (int j = 0; j < 16; j += 2) {
+              const float2 s0 = s_sb[BN / 2 + cc + j], s1 = s_sb[BN / 2 + cc + j + 1];
+              const float y0 = old[j] + fmaf(__uint_as_float(r[j]), s0.x, s0.y);
+              const float y1 = old[j + 1] + fmaf(__uint_as_float(r[j + 1]), s1.x, s1.y);
+              split16x2(valid ? fmaxf(y0, 0.f) : 0.f, valid ? fmaxf(y1, 0.f) : 0.f, hi2[j >> 1], lo2[j >> 1]);
+            }
+            if (in_range) {
+              __half* srow = p.skip16 + ((size_t)b * p.T + t) * (BN / 2) + cc;
+              const size_t splane = (size_t)p.B * p.T * (BN / 2);
+#pragma unroll
+              for (int v = 0; v < 2; ++v) {
+                reinterpret_cast<uint4*>(srow)[v] = make_uint4(hi2[4 * v], hi2[4 * v + 1], hi2[4 * v + 2], hi2[4 * v + 3]);
+                reinterpret_cast<uint4*>(srow + splane)[v] = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
+              }
+            }
+          } else if (in_range) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 sb = s_sb[BN / 2 + cc + j];
               const float y = old[j] + fmaf(__uint_as_float(r[j]), sb.x, sb.y);
-              __stcs(sp0 + (size_t)(c0 + j) * p.T, valid ? y : 0.f);
+              __stcs(sp0 + (size_t)(cc + j) * p.T, valid ? y : 0.f);
             }
           }
         }
