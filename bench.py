@@ -160,10 +160,11 @@ def run_reference(args, arch, B, F, desc, rank, world):
     if rank != 0:
         return
     weights, wdesc = load_weights(arch)
-    threads, rate = best_cpu_threads(arch, weights)                                       # calibration
-    budget = min(12.0, 150.0 / max(1, args.steps + args.warmup))
+    threads, _ = best_cpu_threads(arch, weights)                                          # calibration
+    rate, _, _ = cpu_oracle_rate(arch, weights, 48 if arch == "student" else 96, threads)  # probe at a realistic length
+    budget = min(10.0, 120.0 / max(1, args.steps + args.warmup))
     hop = 256 if arch == "student" else 240
-    frames = int(max(8, min(F, rate * budget / hop)))
+    frames = int(max(8, min(F, 0.7 * rate * budget / hop)))
     for _ in range(args.warmup):
         cpu_oracle_rate(arch, weights, frames, threads)
     tot_s, tot_t = 0, 0.0
@@ -331,9 +332,10 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        threads, rate = best_cpu_threads(arch, weights)
+        threads, _ = best_cpu_threads(arch, weights)
+        rate, _, _ = cpu_oracle_rate(arch, weights, 48 if arch == "student" else 96, threads)
         hop = 256 if arch == "student" else 240
-        frames = int(max(8, min(F, rate * 15.0 / hop)))
+        frames = int(max(8, min(F, 0.7 * rate * 15.0 / hop)))
         r2, n, dt = cpu_oracle_rate(arch, weights, frames, threads)
         cpu = {"value": r2, "unit": "samples/s", "cores": threads, "kind": "port",
                "sample": f"B=1 x {frames} frames ({n} samples, {dt:.1f} s of CPU) of the same synthetic workload; oracle port, torch CPU fp32, {threads} threads"}

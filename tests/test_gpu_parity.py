@@ -10,6 +10,7 @@ from oracle import clarinet_ref as C, heads_ref as W, hifigan_ref as H
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
+MATHS = [pytest.param(0, id="fp32_simt"), pytest.param(1, id="tcgen05_split16")]
 
 
 @pytest.fixture(scope="module")
@@ -17,11 +18,12 @@ def dev():
     return torch.device("cuda:0")
 
 
-def _gen(cfg, sd, dev):
+def _gen(cfg, sd, dev, math=0):
     import tts_cube_b200 as cube
-    g = cube.CubeGenerator(cfg).to(dev)
+    g = cube.CubeGenerator(cfg, math=math).to(dev)
     g.load_state_dict(sd)
     return g.eval()
+
 
 
 # ------------------------------------------------ Path H ------------------------------------------------
@@ -37,13 +39,15 @@ def test_hifigan_golden_mini(dev, name):
     assert err <= 2e-5, f"fp32 SIMT path should sit near fp32 round-off, got {err}"
 
 
-def test_hifigan_golden_trained(dev, neb):
+@pytest.mark.parametrize("math", MATHS)
+def test_hifigan_golden_trained(dev, neb, math):
     sd, cfg = neb
     d = load_golden("hifigan_neb.npz")
-    g = _gen(cfg, sd, dev)
+    g = _gen(cfg, sd, dev, math)
     with torch.no_grad():
         wav, w16 = g.forward_int16(torch.from_numpy(d["mel"]).to(dev))
     err = float(np.abs(wav.cpu().numpy() - d["wav"]).max())
+    print(f"hifigan trained golden math={math}: max-abs {err:.3e} (peak {float(np.abs(d['wav']).max()):.2f})")
     assert err <= TOL, err
     # int16 epilogue: identical wherever the float product is not within fp32 noise of an integer
     ref16 = d["wav_int16"].astype(np.int32)
@@ -57,22 +61,25 @@ def test_hifigan_golden_trained(dev, neb):
     assert torch.equal(w16.cpu(), H.wav_to_int16(wav.cpu()).squeeze(1))
 
 
+@pytest.mark.parametrize("math", MATHS)
 @pytest.mark.parametrize("level", [-5.0, 0.0, 1.0])
-def test_hifigan_trained_loudness_sweep(dev, neb, level):
+def test_hifigan_trained_loudness_sweep(dev, neb, level, math):
     sd, cfg = neb
     mel = H.synthetic_mel(2, 40, seed=1237 + int(level), level=level)
     ref = H.generator_forward(sd, cfg, mel)
-    g = _gen(cfg, sd, dev)
+    g = _gen(cfg, sd, dev, math)
     with torch.no_grad():
         y = g(mel.to(dev)).cpu()
+    print(f"hifigan level={level} math={math}: max-abs {float((y - ref).abs().max()):.3e} (peak {float(ref.abs().max()):.2f})")
     assert float((y - ref).abs().max()) <= TOL
     if level >= 0:
         assert float(ref.abs().max()) > 0.5  # loud: the tolerance check means something
 
 
-def test_hifigan_config_v1_random_weights_ragged(dev):
-    cfg = dict(H.CONFIG_V1, upsample_initial_channel=64)
-    sd = H.random_state_dict(cfg, seed=21, std=0.3, g_scale=0.36)
+@pytest.mark.parametrize("math,c0,gs", [pytest.param(0, 64, 0.36, id="fp32_simt"), pytest.param(1, 512, 0.125, id="tcgen05_split16")])
+def test_hifigan_config_v1_random_weights_ragged(dev, math, c0, gs):
+    cfg = dict(H.CONFIG_V1, upsample_initial_channel=c0)
+    sd = H.random_state_dict(cfg, seed=21, std=0.3, g_scale=gs)
     mel = H.synthetic_mel(3, 21, seed=8)
     frames = [21, 1, 12]
     ref = H.generator_forward_ragged(sd, cfg, mel, frames)
@@ -80,10 +87,11 @@ def test_hifigan_config_v1_random_weights_ragged(dev):
     mel_pad = mel.clone()
     mel_pad[1, :, 1:] = -5.0   # VocoderCollate pads with -5 (cube/io_utils/io_vocoder.py:86): must be ignored
     mel_pad[2, :, 12:] = 7.0
-    g = _gen(cfg, sd, dev)
+    g = _gen(cfg, sd, dev, math)
     with torch.no_grad():
         y = g(mel_pad.to(dev), n_frames=frames).cpu()
     assert y.shape == ref.shape
+    print(f"hifigan v1 ragged math={math}: max-abs {float((y - ref).abs().max()):.3e} (peak {float(ref.abs().max()):.2f})")
     assert float((y - ref).abs().max()) <= TOL
     for b, f in enumerate(frames):
         tail = y[b, 0, H.out_len(cfg, f):]
@@ -130,11 +138,12 @@ def test_hifigan_host_call_matches_device_call(dev):
     assert torch.equal(c, H.wav_to_int16(a))
 
 
-def test_hifigan_full_size_properties(dev, neb):
+@pytest.mark.parametrize("math", MATHS)
+def test_hifigan_full_size_properties(dev, neb, math):
     """BASELINE config 3 shape (10 s utterances) through size-independent properties: batch items are
     independent and a long utterance equals the same utterance inside a padded batch."""
     sd, cfg = neb
-    g = _gen(cfg, sd, dev)
+    g = _gen(cfg, sd, dev, math)
     F = 919
     mel = H.synthetic_mel(2, F, seed=77)
     with torch.no_grad():
@@ -152,6 +161,11 @@ def test_hifigan_full_size_properties(dev, neb):
     pre = H.generator_forward(sd, cfg, mel[:1, :, :64])
     n = H.out_len(cfg, 40)
     assert float((y2[0, 0, :n].cpu() - pre[0, 0, :n]).abs().max()) <= TOL
+    if math == 1:   # tensor-core path against the fp32 path over the whole 10 s
+        with torch.no_grad():
+            ys = _gen(cfg, sd, dev, 0)(mel.to(dev))
+        print(f"hifigan 10 s tc-vs-fp32: max-abs {float((y2 - ys).abs().max()):.3e}")
+        assert float((y2 - ys).abs().max()) <= 2e-4
 
 
 # ------------------------------------------------ Path C ------------------------------------------------
@@ -159,8 +173,6 @@ def _student(ssd, tsd, dev, math=0):
     import tts_cube_b200 as cube
     return cube.ParallelWaveNetVocoder(ssd, tsd, math=math).to(dev).eval()
 
-
-MATHS = [pytest.param(0, id="fp32_simt"), pytest.param(1, id="tcgen05_split16")]
 
 
 def test_upsample2_golden(dev):

@@ -65,6 +65,8 @@ struct TcPacked {
   float* inv_scale = nullptr;
   float* bias = nullptr;
   int N = 0, n_tiles = 0, nchunks_total = 0, nseg = 0;
+  int bn = 256, nphase = 1;
+  long long w_phase_stride = 0;
   tc::TcSeg seg[2];
 };
 
@@ -100,6 +102,9 @@ struct cube_voc {
   PackedConv conv_pre, conv_post_w;
   std::vector<PackedConv> ups;
   std::vector<std::vector<PackedConv>> rb_c1, rb_c2;  // [resblock idx][dilation idx]
+  TcPacked tc_conv_pre;
+  std::vector<TcPacked> tc_ups;
+  std::vector<std::vector<TcPacked>> tc_c1, tc_c2;
   // ClariNet packed layers
   struct Flow {
     PackedConv front, final1, final3;
@@ -255,38 +260,47 @@ static int dev_upload_bytes(cube_voc* h, const void* src, size_t bytes, void** o
   return 0;
 }
 
-static int pack_tc(cube_voc* h, const std::vector<float>& dense, const std::vector<float>& bias, int N, int nchunks,
-                   TcPacked* out) {
+static int pack_tc_multi(cube_voc* h, const std::vector<std::vector<float>>& dense, const std::vector<float>& bias, int N,
+                         int nchunks, int bn, TcPacked* out) {
   using namespace tc;
-  if (N % BN) return fail("tensor-core path needs N %% %d == 0 (got %d)", BN, N);
-  const int Kp = nchunks * BK;
-  out->N = N; out->n_tiles = N / BN; out->nchunks_total = nchunks;
-  std::vector<__half> img((size_t)out->n_tiles * nchunks * 2 * BN * BK);
+  if (N % bn) return fail("tensor-core path needs N %% %d == 0 (got %d)", bn, N);
+  const int Kp = nchunks * BK, nph = (int)dense.size();
+  out->N = N; out->bn = bn; out->n_tiles = N / bn; out->nchunks_total = nchunks; out->nphase = nph;
+  out->w_phase_stride = (long long)out->n_tiles * nchunks * 2 * bn * BK;
+  std::vector<__half> img((size_t)nph * out->w_phase_stride);
   std::vector<float> inv(N);
   for (int n = 0; n < N; ++n) {
     float mx = 0.f;
-    for (int k = 0; k < Kp; ++k) mx = std::max(mx, fabsf(dense[(size_t)n * Kp + k]));
+    for (int ph = 0; ph < nph; ++ph)
+      for (int k = 0; k < Kp; ++k) mx = std::max(mx, fabsf(dense[ph][(size_t)n * Kp + k]));
     int e = 0;
     if (mx > 0.f) { int ex; frexpf(mx, &ex); e = 12 - ex; }   // mx*2^e in [2^11, 2^12)
     const float sc = ldexpf(1.f, e);
     inv[n] = ldexpf(1.f, -e);
-    const int nt = n / BN, r = n % BN;
-    for (int ch = 0; ch < nchunks; ++ch)
-      for (int kk = 0; kk < BK; ++kk) {
-        const float w = dense[(size_t)n * Kp + ch * BK + kk] * sc;
-        const __half hi = __float2half_rn(w);
-        const __half lo = __float2half_rn(w - __half2float(hi));
-        const size_t off = (size_t)swz_off(r, kk);
-        const size_t base = ((size_t)(nt * nchunks + ch) * 2) * (BN * BK);
-        img[base + off] = hi;
-        img[base + (size_t)BN * BK + off] = lo;
-      }
+    const int nt = n / bn, r = n % bn;
+    for (int ph = 0; ph < nph; ++ph)
+      for (int ch = 0; ch < nchunks; ++ch)
+        for (int kk = 0; kk < BK; ++kk) {
+          const float w = dense[ph][(size_t)n * Kp + ch * BK + kk] * sc;
+          const __half hi = __float2half_rn(w);
+          const __half lo = __float2half_rn(w - __half2float(hi));
+          const size_t off = (size_t)swz_off(r, kk);
+          const size_t base = (size_t)ph * out->w_phase_stride + ((size_t)(nt * nchunks + ch) * 2) * (bn * BK);
+          img[base + off] = hi;
+          img[base + (size_t)bn * BK + off] = lo;
+        }
   }
   void* d;
   if (dev_upload_bytes(h, img.data(), img.size() * sizeof(__half), &d)) return 1;
   out->Wimg = (__half*)d;
   if (dev_upload(h, inv, &out->inv_scale)) return 1;
   return dev_upload(h, bias, &out->bias);
+}
+
+static int pack_tc(cube_voc* h, const std::vector<float>& dense, const std::vector<float>& bias, int N, int nchunks,
+                   TcPacked* out) {
+  std::vector<std::vector<float>> d1(1, dense);
+  return pack_tc_multi(h, d1, bias, N, nchunks, tc::BN, out);
 }
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -313,6 +327,43 @@ static int make_tmap_hl16(CUtensorMap* tm, const __half* base, int B, int T, int
                   tc::BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for [2*%d][%d][%d]", (int)r, B, T, C);
+  return 0;
+}
+
+// Conv1d weight [M][C][K] -> tcgen05 images; K order = tap-major, channels padded to BK per tap
+static int pack_tc_conv1d(cube_voc* h, const std::string& base, int M, int C, int K, TcPacked* out) {
+  using namespace tc;
+  HostTensor w; const HostTensor* b;
+  if (get_weight(h, base, &w) || expect_shape(base, w, {M, C, K}) || get_bias(h, base, M, &b)) return 1;
+  const int cpt = (C + BK - 1) / BK, Cp = cpt * BK, nch = K * cpt, Kp = nch * BK;
+  std::vector<std::vector<float>> D(1, std::vector<float>((size_t)M * Kp, 0.f));
+  for (int m = 0; m < M; ++m)
+    for (int c = 0; c < C; ++c)
+      for (int k = 0; k < K; ++k) D[0][(size_t)m * Kp + (size_t)k * Cp + c] = w.data[((size_t)m * C + c) * K + k];
+  if (pack_tc_multi(h, D, b->data, M, nch, std::min(256, M), out)) return 1;
+  out->nseg = 1;
+  out->seg[0] = {K, 1, 0, cpt, ((C - (cpt - 1) * BK) + 15) / 16};
+  return 0;
+}
+
+// ConvTranspose1d weight [C][M][K], stride u: phase r uses taps k = r + (J-1-jj)*u at source row q-(J-1)+jj
+static int pack_tc_convT(cube_voc* h, const std::string& base, int C, int M, int K, int u, TcPacked* out) {
+  using namespace tc;
+  HostTensor w; const HostTensor* b;
+  if (get_weight(h, base, &w) || expect_shape(base, w, {C, M, K}) || get_bias(h, base, M, &b)) return 1;
+  if (C % BK) return fail("tensor-core transposed conv needs C %% %d == 0", BK);
+  const int J = (K + u - 1) / u, cpt = C / BK, nch = J * cpt, Kp = nch * BK;
+  std::vector<std::vector<float>> D(u, std::vector<float>((size_t)M * Kp, 0.f));
+  for (int r = 0; r < u; ++r)
+    for (int jj = 0; jj < J; ++jj) {
+      const int k = r + (J - 1 - jj) * u;
+      if (k >= K) continue;
+      for (int m = 0; m < M; ++m)
+        for (int c = 0; c < C; ++c) D[r][(size_t)m * Kp + (size_t)jj * C + c] = w.data[((size_t)c * M + m) * K + k];
+    }
+  if (pack_tc_multi(h, D, b->data, M, nch, std::min(256, M), out)) return 1;
+  out->nseg = 1;
+  out->seg[0] = {J, 1, -(J - 1), cpt, BK / 16};
   return 0;
 }
 
@@ -459,7 +510,32 @@ static int finalize_hifigan(cube_voc* h) {
       }
     }
   }
-  return pack_small(h, "conv_post", 1, ch, 7, &h->conv_post_w);
+  if (pack_small(h, "conv_post", 1, ch, 7, &h->conv_post_w)) return 1;
+  if (c.math == CUBE_MATH_TC_SPLIT16) {
+    if (c.resblock_type != 1) return fail("tensor-core HiFi-GAN path supports resblock '1' only (use CUBE_MATH_FP32_SIMT)");
+    auto okc = [](int n) { return n == 32 || n == 64 || n == 128 || n == 256 || n == 512; };
+    if (!okc(C0) || (C0 >> c.n_ups) < 32) return fail("tensor-core HiFi-GAN path needs channels in {32..512} (C0=%d)", C0);
+    if (c.num_mels % 8) return fail("tensor-core path needs num_mels %% 8 == 0");
+    if (pack_tc_conv1d(h, "conv_pre", C0, c.num_mels, 7, &h->tc_conv_pre)) return 1;
+    h->tc_ups.resize(c.n_ups);
+    h->tc_c1.assign(c.n_ups * nk, {});
+    h->tc_c2.assign(c.n_ups * nk, {});
+    int cc = C0;
+    for (int i = 0; i < c.n_ups; ++i) {
+      if (pack_tc_convT(h, "ups." + std::to_string(i), cc, cc / 2, c.upsample_kernel_sizes[i], c.upsample_rates[i], &h->tc_ups[i])) return 1;
+      cc /= 2;
+      for (int j = 0; j < nk; ++j) {
+        const int idx = i * nk + j, k = c.resblock_kernel_sizes[j], nd = c.n_dilations[j];
+        h->tc_c1[idx].resize(nd); h->tc_c2[idx].resize(nd);
+        for (int m = 0; m < nd; ++m) {
+          const std::string rb = "resblocks." + std::to_string(idx);
+          if (pack_tc_conv1d(h, rb + ".convs1." + std::to_string(m), cc, cc, k, &h->tc_c1[idx][m])) return 1;
+          if (pack_tc_conv1d(h, rb + ".convs2." + std::to_string(m), cc, cc, k, &h->tc_c2[idx][m])) return 1;
+        }
+      }
+    }
+  }
+  return 0;
 }
 
 static int finalize_student(cube_voc* h) {
@@ -622,9 +698,13 @@ static int upload_lens(cube_voc* h, const int32_t* n_frames, int B, int64_t Fmax
   return 0;
 }
 
+static int forward_hifigan_tc(cube_voc* h, const float* mel, const int32_t* n_frames, float* wav, int16_t* wav16,
+                              int B, int64_t Fmax, cudaStream_t st);
+
 static int forward_hifigan(cube_voc* h, const float* mel, const int32_t* n_frames, float* wav, int16_t* wav16,
                            int B, int64_t Fmax, cudaStream_t st) {
   const cube_voc_config& c = h->cfg;
+  if (c.math == CUBE_MATH_TC_SPLIT16) return forward_hifigan_tc(h, mel, n_frames, wav, wav16, B, Fmax, st);
   const int nU = c.n_ups, nk = c.n_resblock_kernels;
   std::vector<int64_t> L(nU + 1);
   for (int i = 0; i <= nU; ++i) L[i] = hifigan_len(c, Fmax, i);
@@ -741,6 +821,152 @@ static int forward_hifigan(cube_voc* h, const float* mel, const int32_t* n_frame
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward: HiFi-GAN on tensor cores.  Every MMA-input tensor is stored leaky-ReLU'd (slope 0.1) as
+// fp16 hi/lo planes, channels-last; the residual stream is recovered from it by the inverse map.
+// ------------------------------------------------------------------------------------------------
+template <int TN>
+static void launch_tc_t(cube_voc* h, tc::TcParams& tp, cudaStream_t st) {
+  static bool attr[64] = {false};
+  if (!attr[h->device & 63]) {
+    cudaFuncSetAttribute(tc::tc_conv_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<TN>::SMEM);
+    attr[h->device & 63] = true;
+  }
+  const long long tiles = (long long)tp.n_tiles * tp.t_tiles * tp.B * (tp.nphase > 0 ? tp.nphase : 1);
+  const int grid = (int)std::min<long long>(tiles, h->sm_count);
+  tc::tc_conv_kernel<TN><<<grid, tc::NUM_THREADS, tc::Cfg<TN>::SMEM, st>>>(tp);
+}
+
+static void launch_tc_bn(cube_voc* h, int bn, tc::TcParams& tp, cudaStream_t st) {
+  if (bn == 256) launch_tc_t<256>(h, tp, st);
+  else if (bn == 128) launch_tc_t<128>(h, tp, st);
+  else if (bn == 64) launch_tc_t<64>(h, tp, st);
+  else launch_tc_t<32>(h, tp, st);
+}
+
+static int forward_hifigan_tc(cube_voc* h, const float* mel, const int32_t* n_frames, float* wav, int16_t* wav16,
+                              int B, int64_t Fmax, cudaStream_t st) {
+  const cube_voc_config& c = h->cfg;
+  const int nU = c.n_ups, nk = c.n_resblock_kernels;
+  std::vector<int64_t> L(nU + 1);
+  for (int i = 0; i <= nU; ++i) L[i] = hifigan_len(c, Fmax, i);
+  if (L[nU] > 0x7fffffffLL / 2) return fail("utterance too long");
+  if (upload_lens(h, n_frames, B, Fmax, nU + 1, st)) return 1;
+  const int C0 = c.upsample_initial_channel;
+  size_t stage_max = (size_t)C0 * L[0];
+  for (int i = 0; i < nU; ++i) stage_max = std::max(stage_max, (size_t)(C0 >> (i + 1)) * L[i + 1]);
+  float *p0, *p1, *p2, *p3, *xs, *m16;
+  // four fp16-plane buffers (2 planes x 2 B = 4 B/element, i.e. one fp32 tensor each) + the fp32 ResBlock sum
+  if (ws_get(h, "gP0", stage_max * B, &p0) || ws_get(h, "gP1", stage_max * B, &p1) || ws_get(h, "gP2", stage_max * B, &p2) ||
+      ws_get(h, "gP3", stage_max * B, &p3) || ws_get(h, "gXS", stage_max * B, &xs) ||
+      ws_get(h, "gMel16", (size_t)B * Fmax * c.num_mels, &m16)) return 1;
+  __half *P0 = (__half*)p0, *P1 = (__half*)p1, *P2 = (__half*)p2, *P3 = (__half*)p3, *M16 = (__half*)m16;
+  Launcher lx{h, st};
+  const float LR = 0.1f;
+  auto base_params = [&](const TcPacked& pk, const __half* A, int La, int Ca, int Q, int Lout, int Cout, const int* lens,
+                         tc::TcParams& tp) -> int {
+    memset(&tp, 0, sizeof(tp));
+    if (make_tmap_hl16(&tp.tmA[0], A, B, La, Ca)) return 1;
+    tp.tmA[1] = tp.tmA[0];
+    tp.Wimg = pk.Wimg; tp.inv_scale = pk.inv_scale; tp.bias = pk.bias;
+    tp.nseg = 1; tp.seg[0] = pk.seg[0]; tp.nchunks_total = pk.nchunks_total;
+    tp.B = B; tp.T = Q; tp.n_tiles = pk.n_tiles; tp.t_tiles = (Q + tc::BM - 1) / tc::BM;
+    tp.lens = lens; tp.epi = tc::TC_EPI_CONV; tp.outC = Cout; tp.L_out = Lout;
+    tp.nphase = pk.nphase; tp.w_phase_stride = pk.w_phase_stride; tp.ostride = 1;
+    tp.out_slope = LR; tp.res_inv_slope = 1.f / LR; tp.acc_div = 1.f;
+    return 0;
+  };
+  {  // mel -> fp16 planes (pad frames masked), then conv_pre; its output is stored lrelu'd for ups[0]
+    lx.begin("to_hl16");
+    tc::to_hl16_kernel<<<dim3(((int)Fmax + 31) / 32, (c.num_mels + 31) / 32, B), 256, 0, st>>>(mel, M16, B, c.num_mels, (int)Fmax, h->d_lens);
+    lx.check();
+    lx.end();
+    lx.begin("conv_pre");
+    tc::TcParams tp;
+    if (base_params(h->tc_conv_pre, M16, (int)L[0], c.num_mels, (int)L[0], (int)L[0], C0, h->d_lens, tp)) return 1;
+    tp.seg[0].dil = 1; tp.seg[0].off0 = -3;
+    tp.out16 = P0;
+    launch_tc_bn(h, h->tc_conv_pre.bn, tp, st);
+    lx.check();
+    lx.end();
+  }
+  int ch = C0;
+  for (int i = 0; i < nU; ++i) {
+    const int u = c.upsample_rates[i], K = c.upsample_kernel_sizes[i], pad = (K - u) / 2;
+    const int Lin = (int)L[i], Lo = (int)L[i + 1], cho = ch / 2;
+    const int* lens_out = h->d_lens + (size_t)(i + 1) * B;
+    __half *IN = P0, *U = P1, *T1 = P2, *R = P3, *NX = P0;
+    {  // U = lrelu(ups[i](IN))   (IN already holds lrelu(x))
+      lx.begin("ups");
+      tc::TcParams tp;
+      if (base_params(h->tc_ups[i], IN, Lin, ch, (Lo - 1 + pad) / u + 1, Lo, cho, lens_out, tp)) return 1;
+      tp.ostride = u;
+      for (int r = 0; r < u; ++r) tp.ooff[r] = r - pad;
+      tp.out16 = U;
+      launch_tc_bn(h, h->tc_ups[i].bn, tp, st);
+      lx.check();
+      lx.end();
+    }
+    ch = cho;
+    const bool last_stage = (i == nU - 1);
+    if (nk == 1) CU_TRY(cudaMemsetAsync(xs, 0, (size_t)B * ch * Lo * sizeof(float), st));   // (0 + v)/1
+    for (int j = 0; j < nk; ++j) {
+      const int idx = i * nk + j, k = c.resblock_kernel_sizes[j], nd = c.n_dilations[j];
+      const int accm = (nk == 1) ? tc::TC_ACC_ADD_DIV : (j == 0 ? tc::TC_ACC_SET : (j == nk - 1 ? tc::TC_ACC_ADD_DIV : tc::TC_ACC_ADD));
+      const __half* xcur = U;
+      for (int m = 0; m < nd; ++m) {
+        const int d = c.resblock_dilations[j][m];
+        {
+          lx.begin("rb_conv1");
+          tc::TcParams tp;
+          if (base_params(h->tc_c1[idx][m], xcur, Lo, ch, Lo, Lo, ch, lens_out, tp)) return 1;
+          tp.seg[0].dil = d; tp.seg[0].off0 = -((k * d - d) / 2);
+          tp.out16 = T1;
+          launch_tc_bn(h, h->tc_c1[idx][m].bn, tp, st);
+          lx.check();
+          lx.end();
+        }
+        {
+          lx.begin("rb_conv2");
+          tc::TcParams tp;
+          if (base_params(h->tc_c2[idx][m], T1, Lo, ch, Lo, Lo, ch, lens_out, tp)) return 1;
+          tp.seg[0].dil = 1; tp.seg[0].off0 = -((k - 1) / 2);
+          tp.res16 = xcur;
+          const bool last = (m == nd - 1);
+          if (!last) {
+            tp.out16 = R;
+          } else {
+            tp.acc32 = xs; tp.acc_mode = accm; tp.acc_div = (float)nk;
+            if (accm == tc::TC_ACC_ADD_DIV) {
+              if (nk == 1) tp.acc_mode = tc::TC_ACC_ADD_DIV;   // (0 + v)/1
+              tp.acc_store = last_stage ? 1 : 0;               // conv_post reads the fp32 sum
+              tp.out16b = last_stage ? nullptr : NX;           // next ups reads lrelu(x) planes
+            }
+          }
+          launch_tc_bn(h, h->tc_c2[idx][m].bn, tp, st);
+          lx.check();
+          lx.end();
+          xcur = R;
+        }
+      }
+    }
+  }
+  {  // x = tanh(conv_post(leaky_relu(x)))  - default slope 0.01   (hifigan/models.py:112-114)
+    lx.begin("conv_post");
+    const int Lo = (int)L[nU];
+    SmallP p;
+    memset(&p, 0, sizeof(p));
+    p.src = xs; p.bstride = (long long)ch * Lo; p.C = ch; p.L = Lo;
+    p.taps = 7; p.dil = 1; p.off0 = -3; p.preact = PRE_LRELU; p.slope = 0.01f;
+    p.W = h->conv_post_w.W; p.bias = h->conv_post_w.bias;
+    p.out_lens = h->d_lens + (size_t)nU * B; p.L_out = Lo;
+    p.out = wav; p.out_bstride = Lo; p.out_i16 = wav16; p.epi = SEPI_TANH;
+    lx.small(p, B, 1);
+    lx.end();
+  }
+  return lx.err;
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward: ClariNet IAF student
 // ------------------------------------------------------------------------------------------------
 static int dilation_of(const cube_voc_config& c, int i) {
@@ -807,7 +1033,7 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
     if (make_tmap_hl16(&tm_h, h16, B, T, R) || make_tmap_hl16(&tm_o, o16, B, T, G) || make_tmap_hl16(&tm_c, c16, B, T, CI)) return 1;
     static bool attr[64] = {false};
     if (!attr[h->device & 63]) {
-      CU_TRY(cudaFuncSetAttribute(tc::tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+      CU_TRY(cudaFuncSetAttribute(tc::tc_conv_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<256>::SMEM));
       attr[h->device & 63] = true;
     }
     lx.begin("to_hl16");
@@ -822,7 +1048,8 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
     tp.lens = lens_T;
     const long long tiles = (long long)tp.n_tiles * tp.t_tiles * B;
     const int grid = (int)std::min<long long>(tiles, h->sm_count);
-    tc::tc_conv_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(tp);
+    tp.nphase = 1;
+    tc::tc_conv_kernel<256><<<grid, tc::NUM_THREADS, tc::Cfg<256>::SMEM, st>>>(tp);
     lx.check();
   };
   for (int f = 0; f < c.n_flows; ++f) {

@@ -45,10 +45,20 @@ __host__ __device__ constexpr int swz_off(int r, int k) {
                     : r * 32 + (((k / 8) ^ ((r >> 1) & 3)) * 8) + (k % 8);
 }
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BN * 8 /*scale,bias*/;
+// per-N-tile-width variants (HiFi-GAN stages have 256/128/64/32 output channels)
+template <int TN> struct Cfg {
+  static_assert(TN == 256 || TN == 128 || TN == 64 || TN == 32, "tile N");
+  static constexpr int B_BYTES = TN * BK * 2;
+  static constexpr int STAGE = 2 * A_TILE_BYTES + 2 * B_BYTES;
+  static constexpr int NSTAGE = (190 * 1024 / STAGE) > 8 ? 8 : (190 * 1024 / STAGE);
+  static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256 + TN * 8;
+  static constexpr int TMEM_COLS = (2 * TN < 32) ? 32 : 2 * TN;
+};
 constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
 
-enum { TC_EPI_GATE = 0, TC_EPI_RESSKIP = 1, TC_EPI_FINAL = 2 };
+enum { TC_EPI_GATE = 0, TC_EPI_RESSKIP = 1, TC_EPI_FINAL = 2, TC_EPI_CONV = 3 };
+enum { TC_ACC_NONE = 0, TC_ACC_SET = 1, TC_ACC_ADD = 2, TC_ACC_ADD_DIV = 3 };
 
 struct TcSeg {
   int taps, dil, off0;   // source row of output row t, tap j: t + off0 + j*dil
@@ -79,6 +89,19 @@ struct TcParams {
   //   z_out[t+1] = z_in[t+1]*exp(logs[t]) + mu[t], z_out[0] = 0
   const float* w3;          // [2][128] + bias [2]
   const float* z_in; float* z_out;   // [B][T]
+  // TC_EPI_CONV (HiFi-GAN convs; every A-operand tensor holds leaky-ReLU'd values a = lrelu(x)):
+  //   v = acc*inv_scale + bias (+ x_res, x_res = inverse-lrelu of res16 at the same row/col)
+  //   out16 (if set)  <- lrelu(v, out_slope) as fp16 planes [2][B][L_out][outC]
+  //   acc32 (if set)  : fp32 [B][outC][L_out] channel-first; SET: =v, ADD: +=v,
+  //                     ADD_DIV: y=(acc+v)/acc_div -> acc32 (if acc_store) and out16b <- lrelu(y, out_slope)
+  int nphase;               // transposed conv: output phases (weights per phase), else 1
+  long long w_phase_stride; // fp16 elements between phase weight sets
+  int ostride, ooff[8];     // output row of tile row q, phase r: q*ostride + ooff[r]
+  int L_out;                // output rows per batch item; T = rows of q per batch item
+  const __half* res16; float res_inv_slope;   // residual source planes [2][B][L_out][outC], 1/slope it was stored with
+  float out_slope;
+  float* acc32; int acc_mode; float acc_div; int acc_store;
+  __half* out16b;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -182,9 +205,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return d;
 }
 
-// instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=BN
-__host__ __device__ constexpr uint32_t make_idesc() {
-  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 __device__ __forceinline__ __half f2h_sat(float x) {
@@ -203,6 +226,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
 }
 __device__ __forceinline__ float ex2_fast(float x) {
   float y;
@@ -234,7 +262,12 @@ __device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+template <int TN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcParams p) {
+  constexpr int STAGES = Cfg<TN>::NSTAGE;
+  constexpr int STAGE_BYTES = Cfg<TN>::STAGE;
+  constexpr int B_TILE_BYTES = Cfg<TN>::B_BYTES;
+  constexpr int BN = TN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -246,7 +279,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
   float2* s_sb = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 256);   // [BN] (inv_scale, bias) of this tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.n_tiles * p.t_tiles * p.B;
+  const int nphase = p.nphase > 0 ? p.nphase : 1;
+  const int total_tiles = p.n_tiles * p.t_tiles * p.B * nphase;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA[0]);
@@ -255,7 +289,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], NUM_EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg<TN>::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -267,10 +301,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
-        const int rest = tile / p.n_tiles;
+        int rest = tile / p.n_tiles;
+        const int ph = rest % nphase; rest /= nphase;
         const int tt = rest % p.t_tiles, b = rest / p.t_tiles;
         const int t0 = tt * BM;
-        const __half* wt = p.Wimg + (size_t)nt * p.nchunks_total * 2 * (BN * BK);
+        const __half* wt = p.Wimg + (size_t)ph * p.w_phase_stride + (size_t)nt * p.nchunks_total * 2 * (BN * BK);
         int chunk = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const TcSeg sg = p.seg[s];
@@ -295,7 +330,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc();
+      constexpr uint32_t idesc = make_idesc(TN);
       uint32_t it = 0, titer = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
         const uint32_t acc = titer & 1, aph = (titer >> 1) & 1;
@@ -340,7 +375,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
     uint32_t titer = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
       const int nt = tile % p.n_tiles;
-      const int rest = tile / p.n_tiles;
+      int rest = tile / p.n_tiles;
+      const int ph = rest % nphase; rest /= nphase;
       const int tt = rest % p.t_tiles, b = rest / p.t_tiles;
       const int t = tt * BM + row;
       const uint32_t acc = titer & 1, aph = (titer >> 1) & 1;
@@ -362,6 +398,95 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
       const int len = p.lens ? min(p.lens[b], p.T) : p.T;
       const bool in_range = t < p.T;
       const bool valid = t < len;
+      if (p.epi == TC_EPI_CONV) {
+        // ---- HiFi-GAN convolution epilogue: bias, residual, leaky-ReLU, ResBlock averaging ----
+        constexpr int CPS = BN / 4;                       // columns per epilogue sub-group
+        constexpr int CW = CPS < 16 ? CPS : 16;           // columns per TMEM load
+        const int t_out = t * p.ostride + p.ooff[ph];
+        const int olen = p.lens ? min(p.lens[b], p.L_out) : p.L_out;
+        const bool o_in = in_range && t_out >= 0 && t_out < p.L_out;
+        const bool o_valid = o_in && t_out < olen;
+        const size_t rowoff = ((size_t)b * p.L_out + (o_in ? t_out : 0)) * p.outC + nt * BN;
+        const size_t plane = (size_t)p.B * p.L_out * p.outC;
+#pragma unroll
+        for (int cc = sub * CPS; cc < sub * CPS + CPS; cc += CW) {
+          uint32_t r[CW];
+          if constexpr (CW == 16) tmem_ld16(taddr + cc, r); else tmem_ld8(taddr + cc, r);
+          uint32_t rh[CW / 2], rl[CW / 2];
+          float old[CW];
+          if (p.res16 && o_in) {
+#pragma unroll
+            for (int v = 0; v < CW / 8; ++v) {
+              const uint4 a = reinterpret_cast<const uint4*>(p.res16 + rowoff + cc)[v];
+              const uint4 c = reinterpret_cast<const uint4*>(p.res16 + plane + rowoff + cc)[v];
+              rh[4 * v] = a.x; rh[4 * v + 1] = a.y; rh[4 * v + 2] = a.z; rh[4 * v + 3] = a.w;
+              rl[4 * v] = c.x; rl[4 * v + 1] = c.y; rl[4 * v + 2] = c.z; rl[4 * v + 3] = c.w;
+            }
+          } else {
+#pragma unroll
+            for (int v = 0; v < CW / 2; ++v) rh[v] = rl[v] = 0u;
+          }
+          if (p.acc32 && p.acc_mode >= TC_ACC_ADD && o_in) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) old[j] = __ldcs(p.acc32 + ((size_t)b * p.outC + nt * BN + cc + j) * p.L_out + t_out);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) old[j] = 0.f;
+          }
+          tmem_ld_wait();
+          float v[CW];
+#pragma unroll
+          for (int j = 0; j < CW; j += 2) {
+            const float2 s0 = s_sb[cc + j], s1 = s_sb[cc + j + 1];
+            const float2 ah = unpack_h2(rh[j >> 1]), al = unpack_h2(rl[j >> 1]);
+            float a0 = ah.x + al.x, a1 = ah.y + al.y;           // a = lrelu(x_res): invert
+            a0 = a0 < 0.f ? a0 * p.res_inv_slope : a0;
+            a1 = a1 < 0.f ? a1 * p.res_inv_slope : a1;
+            v[j] = o_valid ? fmaf(__uint_as_float(r[j]), s0.x, s0.y) + a0 : 0.f;
+            v[j + 1] = o_valid ? fmaf(__uint_as_float(r[j + 1]), s1.x, s1.y) + a1 : 0.f;
+          }
+          if (p.out16 && o_in) {
+            uint32_t hi2[CW / 2], lo2[CW / 2];
+#pragma unroll
+            for (int j = 0; j < CW; j += 2) {
+              const float y0 = v[j] < 0.f ? v[j] * p.out_slope : v[j], y1 = v[j + 1] < 0.f ? v[j + 1] * p.out_slope : v[j + 1];
+              split16x2(y0, y1, hi2[j >> 1], lo2[j >> 1]);
+            }
+#pragma unroll
+            for (int q4 = 0; q4 < CW / 8; ++q4) {
+              reinterpret_cast<uint4*>(p.out16 + rowoff + cc)[q4] = make_uint4(hi2[4 * q4], hi2[4 * q4 + 1], hi2[4 * q4 + 2], hi2[4 * q4 + 3]);
+              reinterpret_cast<uint4*>(p.out16 + plane + rowoff + cc)[q4] = make_uint4(lo2[4 * q4], lo2[4 * q4 + 1], lo2[4 * q4 + 2], lo2[4 * q4 + 3]);
+            }
+          }
+          if (p.acc32 && o_in) {
+            if (p.acc_mode == TC_ACC_ADD_DIV) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) v[j] = o_valid ? (old[j] + v[j]) / p.acc_div : 0.f;
+              if (p.acc_store) {
+#pragma unroll
+                for (int j = 0; j < CW; ++j) __stcs(p.acc32 + ((size_t)b * p.outC + nt * BN + cc + j) * p.L_out + t_out, v[j]);
+              }
+              if (p.out16b) {
+                uint32_t hi2[CW / 2], lo2[CW / 2];
+#pragma unroll
+                for (int j = 0; j < CW; j += 2) {
+                  const float y0 = v[j] < 0.f ? v[j] * p.out_slope : v[j], y1 = v[j + 1] < 0.f ? v[j + 1] * p.out_slope : v[j + 1];
+                  split16x2(y0, y1, hi2[j >> 1], lo2[j >> 1]);
+                }
+#pragma unroll
+                for (int q4 = 0; q4 < CW / 8; ++q4) {
+                  reinterpret_cast<uint4*>(p.out16b + rowoff + cc)[q4] = make_uint4(hi2[4 * q4], hi2[4 * q4 + 1], hi2[4 * q4 + 2], hi2[4 * q4 + 3]);
+                  reinterpret_cast<uint4*>(p.out16b + plane + rowoff + cc)[q4] = make_uint4(lo2[4 * q4], lo2[4 * q4 + 1], lo2[4 * q4 + 2], lo2[4 * q4 + 3]);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) __stcs(p.acc32 + ((size_t)b * p.outC + nt * BN + cc + j) * p.L_out + t_out, old[j] + v[j]);
+            }
+          }
+        }
+      }
+      if constexpr (TN == 256) {
       if (p.epi == TC_EPI_GATE) {
         // cols [0,128) filter, [128,256) gate of output channels nt*128 + c; this warp: c in [32*sub, +32)
         //   o = tanh(f)*sigmoid(g) = (E1 - 1) / ((E1 + 1)(1 + E2)),  E1 = e^{2f}, E2 = e^{-g}: 2 ex2 + 1 rcp
@@ -418,7 +543,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
             if (t + 1 < p.T) zo[t + 1] = (t + 1 < len) ? fmaf(p.z_in[(size_t)b * p.T + t + 1], expf(logs), mu) : 0.f;
           }
         }
-      } else if (sub < 2) {
+      } else if (p.epi == TC_EPI_RESSKIP && sub < 2) {
         // cols [0,128): residual stream, updated in place (fp16 planes); this warp: c in [64*sub, +64)
         const size_t plane = (size_t)p.B * p.T * p.hC;
         __half* hrow = p.h16 + ((size_t)b * p.T + t) * p.hC;
@@ -457,7 +582,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
             }
           }
         }
-      } else {
+      } else if (p.epi == TC_EPI_RESSKIP) {
         // cols [128,256): skip accumulator, fp32 [B][128][T]; lanes -> consecutive t: coalesced.
         // this warp: skip channels [64*(sub-2), +64).  All loads of a chunk are issued before the
         // first use (the compiler may not hoist them over the previous column's store by itself).
@@ -503,6 +628,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
           }
         }
       }
+      }  // TN == 256 (ClariNet epilogues)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -512,7 +638,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, Cfg<TN>::TMEM_COLS);
   }
 }
 
@@ -520,13 +646,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
 // fp32 [B][C][T] (channel-first) -> fp16 hi/lo planes [2][B][T][C] (channels-last); tiled transpose
 // through shared memory so both sides are coalesced.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) to_hl16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int B, int C, int T) {
+__global__ void __launch_bounds__(256) to_hl16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int B, int C, int T,
+                                                      const int* __restrict__ lens = nullptr) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int i = ty; i < 32; i += 8) {
     const int c = c0 + i, t = t0 + tx;
-    tile[i][tx] = (c < C && t < T) ? src[((size_t)b * C + c) * T + t] : 0.f;
+    const int tl = lens ? min(lens[blockIdx.z], T) : T;   // rows past the valid length read as zero
+    tile[i][tx] = (c < C && t < tl) ? src[((size_t)b * C + c) * T + t] : 0.f;
   }
   __syncthreads();
   const size_t plane = (size_t)B * T * C;
