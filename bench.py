@@ -217,9 +217,8 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    # auto: tensor cores (split-fp16 x3) for the student's residual stack; HiFi-GAN runs the fp32 path
-    math = {"auto": _lib.MATH_TC_SPLIT16 if arch == "student" else _lib.MATH_FP32_SIMT,
-            "simt": _lib.MATH_FP32_SIMT, "tc": _lib.MATH_TC_SPLIT16}[args.math]
+    # auto: tensor cores (split-fp16 x3) for the dense layers of both vocoders
+    math = {"auto": _lib.MATH_TC_SPLIT16, "simt": _lib.MATH_FP32_SIMT, "tc": _lib.MATH_TC_SPLIT16}[args.math]
     weights, wdesc = load_weights(arch)
     if arch == "student":
         voc = cube.ParallelWaveNetVocoder(weights[0], weights[1], math=math).to(dev)
@@ -321,7 +320,8 @@ def main():
         # resblock convs: 95 % of layer-wise bytes, 96 % of FLOPs
         by = 0.95 * HIFI_BYTES_PER_SAMPLE * samples_per_step
         ach = by / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else None
-        roof = {"kernel": "conv_tile_kernel (ResBlock dilated convs, fused lrelu/bias/residual)", "bound": "hbm",
+        roof = {"kernel": ("conv_tile_kernel (ResBlock dilated convs, fused lrelu/bias/residual, fp32 FFMA2)" if math == 0 else
+                           "tc::tc_conv_kernel<256|128|64|32> TC_EPI_CONV (ResBlock dilated convs on tcgen05, split-fp16 x3)"), "bound": "hbm",
                 "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": (ach / pk["hbm"]) if ach else None, "traffic": None,
                 "launches_per_step": nlaunch, "avg_launch_ms": dom_ms / nlaunch, "algorithmic_bytes_per_launch": by / nlaunch,
                 "share_of_step": dom_ms / (ms / args.steps) if ms > 0 else None, "peak_source": pk["src"] + " copy bandwidth",

@@ -16,7 +16,7 @@ from ._lib import VocConfig, lib
 from .generator import _Handle
 
 
-def student_config(student_sd: Mapping[str, torch.Tensor], math: int = _lib.MATH_FP32_SIMT,
+def student_config(student_sd: Mapping[str, torch.Tensor], math=None,
                    dilation_base: int = 3, dilation_cycle: int = 6,
                    upsample_scales: Sequence[int] = (16, 16)) -> VocConfig:
     nb: Dict[int, int] = {}
@@ -30,6 +30,8 @@ def student_config(student_sd: Mapping[str, torch.Tensor], math: int = _lib.MATH
         else student_sd["iafs.0.res_blocks.0.filter_conv.conv.weight"]
     wc = student_sd.get("iafs.0.res_blocks.0.filter_conv_c.weight_v", student_sd.get("iafs.0.res_blocks.0.filter_conv_c.weight"))
     wf = student_sd.get("iafs.0.front_conv.0.conv.weight_v", student_sd.get("iafs.0.front_conv.0.conv.weight"))
+    if math is None:  # auto: tensor cores for the shipped 128/256/128 geometry, else fp32 kernels
+        math = _lib.MATH_TC_SPLIT16 if (int(w.shape[1]) == 128 and int(w.shape[0]) % 128 == 0) else _lib.MATH_FP32_SIMT
     cfg = VocConfig()
     cfg.arch = _lib.ARCH_PWN_STUDENT
     cfg.math = math
@@ -49,7 +51,7 @@ def student_config(student_sd: Mapping[str, torch.Tensor], math: int = _lib.MATH
 
 class ParallelWaveNetVocoder(torch.nn.Module):
     def __init__(self, student_sd: Mapping[str, torch.Tensor], teacher_sd: Mapping[str, torch.Tensor],
-                 math: int = _lib.MATH_FP32_SIMT, dilation_base: int = 3, dilation_cycle: int = 6):
+                 math=None, dilation_base: int = 3, dilation_cycle: int = 6):
         super().__init__()
         lib()
         self._cfg = student_config(student_sd, math, dilation_base, dilation_cycle)

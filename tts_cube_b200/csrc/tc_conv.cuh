@@ -100,6 +100,9 @@ struct TcParams {
   int L_out;                // output rows per batch item; T = rows of q per batch item
   const __half* res16; float res_inv_slope;   // residual source planes [2][B][L_out][outC], 1/slope it was stored with
   float out_slope;
+  float a_inv_scale;        // 1/S of the A-operand planes (folded into the per-column de-scale); 1 when unscaled
+  float plane_scale;        // S: power-of-two scale of stored activation planes (keeps the fp16 `lo` part out of
+                            // the subnormal range for small activations); residual planes are read back with 1/S
   float* acc32; int acc_mode; float acc_div; int acc_store;
   __half* out16b;
 };
@@ -384,7 +387,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
       // folded in: filter columns carry 2*log2(e) (-> 2^a = e^{2f}), gate columns -log2(e) (-> e^{-g}).
       asm volatile("bar.sync 1, 512;" ::: "memory");   // previous tile's readers are done
       if (etid < BN) {
-        float sc = __ldg(p.inv_scale + nt * BN + etid), bi = __ldg(p.bias + nt * BN + etid);
+        float sc = __ldg(p.inv_scale + nt * BN + etid) * p.a_inv_scale, bi = __ldg(p.bias + nt * BN + etid);
         if (p.epi == TC_EPI_GATE) {
           const float k = etid < BN / 2 ? 2.f * LOG2E : -LOG2E;
           sc *= k; bi *= k;
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
           for (int j = 0; j < CW; j += 2) {
             const float2 s0 = s_sb[cc + j], s1 = s_sb[cc + j + 1];
             const float2 ah = unpack_h2(rh[j >> 1]), al = unpack_h2(rl[j >> 1]);
-            float a0 = ah.x + al.x, a1 = ah.y + al.y;           // a = lrelu(x_res): invert
+            float a0 = (ah.x + al.x) * p.a_inv_scale, a1 = (ah.y + al.y) * p.a_inv_scale;   // a = lrelu(x_res): invert
             a0 = a0 < 0.f ? a0 * p.res_inv_slope : a0;
             a1 = a1 < 0.f ? a1 * p.res_inv_slope : a1;
             v[j] = o_valid ? fmaf(__uint_as_float(r[j]), s0.x, s0.y) + a0 : 0.f;
@@ -450,7 +453,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
 #pragma unroll
             for (int j = 0; j < CW; j += 2) {
               const float y0 = v[j] < 0.f ? v[j] * p.out_slope : v[j], y1 = v[j + 1] < 0.f ? v[j + 1] * p.out_slope : v[j + 1];
-              split16x2(y0, y1, hi2[j >> 1], lo2[j >> 1]);
+              split16x2(y0 * p.plane_scale, y1 * p.plane_scale, hi2[j >> 1], lo2[j >> 1]);
             }
 #pragma unroll
             for (int q4 = 0; q4 < CW / 8; ++q4) {
@@ -471,7 +474,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
 #pragma unroll
                 for (int j = 0; j < CW; j += 2) {
                   const float y0 = v[j] < 0.f ? v[j] * p.out_slope : v[j], y1 = v[j + 1] < 0.f ? v[j + 1] * p.out_slope : v[j + 1];
-                  split16x2(y0, y1, hi2[j >> 1], lo2[j >> 1]);
+                  split16x2(y0 * p.plane_scale, y1 * p.plane_scale, hi2[j >> 1], lo2[j >> 1]);
                 }
 #pragma unroll
                 for (int q4 = 0; q4 < CW / 8; ++q4) {
@@ -647,7 +650,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
 // through shared memory so both sides are coalesced.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) to_hl16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int B, int C, int T,
-                                                      const int* __restrict__ lens = nullptr) {
+                                                      const int* __restrict__ lens = nullptr, float scale = 1.f) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -662,7 +665,7 @@ __global__ void __launch_bounds__(256) to_hl16_kernel(const float* __restrict__ 
     const int t = t0 + i, c = c0 + tx;
     if (t < T && c < C) {
       __half hi, lo;
-      split16(tile[tx][i], hi, lo);
+      split16(tile[tx][i] * scale, hi, lo);
       const size_t o = ((size_t)b * T + t) * C + c;
       dst[o] = hi;
       dst[plane + o] = lo;

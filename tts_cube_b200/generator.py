@@ -116,7 +116,18 @@ class _Handle:
             pass
 
 
-def hifigan_config(h, math: int = _lib.MATH_FP32_SIMT) -> VocConfig:
+def hifigan_tc_supported(h) -> bool:
+    """The tcgen05 path covers ResBlock1 generators whose stage widths are all in {32,...,512}."""
+    c0 = int(_cfg_get(h, "upsample_initial_channel"))
+    n = len(list(_cfg_get(h, "upsample_rates")))
+    widths = [c0 >> i for i in range(n + 1)]
+    return (str(_cfg_get(h, "resblock")) == "1" and all(w in (32, 64, 128, 256, 512) for w in widths)
+            and int(_cfg_get(h, "num_mels", 80) or 80) % 8 == 0)
+
+
+def hifigan_config(h, math=None) -> VocConfig:
+    if math is None:  # auto: tensor cores where the architecture fits, else the fp32 kernels
+        math = _lib.MATH_TC_SPLIT16 if hifigan_tc_supported(h) else _lib.MATH_FP32_SIMT
     cfg = VocConfig()
     cfg.arch = _lib.ARCH_HIFIGAN
     cfg.math = math
@@ -144,7 +155,9 @@ def hifigan_config(h, math: int = _lib.MATH_FP32_SIMT) -> VocConfig:
 class CubeGenerator(torch.nn.Module):
     """B200 replacement for ``hifigan.models.Generator`` (inference)."""
 
-    def __init__(self, h, math: int = _lib.MATH_FP32_SIMT):
+    def __init__(self, h, math=None):
+        """math: None = auto (tcgen05 split-fp16 when the architecture fits, else fp32 FFMA),
+        _lib.MATH_FP32_SIMT or _lib.MATH_TC_SPLIT16 to force one."""
         super().__init__()
         self.h = h
         self._cfg = hifigan_config(h, math)
@@ -223,7 +236,7 @@ class CubeGenerator(torch.nn.Module):
         return hd.forward_host(mel.contiguous(), n_frames, None, out)
 
 
-def install_into_cubegan(model, math: int = _lib.MATH_FP32_SIMT):
+def install_into_cubegan(model, math=None):
     """Replace ``model._generator`` (reference cube/networks/cubegan.py:43) by a CubeGenerator that
     carries the same weights, on the same device.  ``model.inference`` then runs unchanged."""
     ref = model._generator
