@@ -824,16 +824,46 @@ static int forward_hifigan(cube_voc* h, const float* mel, const int32_t* n_frame
 // forward: HiFi-GAN on tensor cores.  Every MMA-input tensor is stored leaky-ReLU'd (slope 0.1) as
 // fp16 hi/lo planes, channels-last; the residual stream is recovered from it by the inverse map.
 // ------------------------------------------------------------------------------------------------
+static bool use_cg2() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CUBE_TC_CG2"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+// tp.T = rows per batch item; fills t_tiles for the chosen variant and launches
 template <int TN>
 static void launch_tc_t(cube_voc* h, tc::TcParams& tp, cudaStream_t st) {
+  const int nph = tp.nphase > 0 ? tp.nphase : 1;
+  if (use_cg2()) {
+    static bool attr2[64] = {false};
+    if (!attr2[h->device & 63]) {
+      cudaFuncSetAttribute(tc::tc_conv_kernel<TN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<TN, true>::SMEM);
+      attr2[h->device & 63] = true;
+    }
+    tp.t_tiles = (tp.T + 2 * tc::BM - 1) / (2 * tc::BM);
+    const long long tiles = (long long)tp.n_tiles * tp.t_tiles * tp.B * nph;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * (unsigned)std::min<long long>(tiles, h->sm_count / 2));
+    cfg.blockDim = dim3(tc::NUM_THREADS);
+    cfg.dynamicSmemBytes = tc::Cfg<TN, true>::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, tc::tc_conv_kernel<TN, true>, tp);
+    return;
+  }
   static bool attr[64] = {false};
   if (!attr[h->device & 63]) {
-    cudaFuncSetAttribute(tc::tc_conv_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<TN>::SMEM);
+    cudaFuncSetAttribute(tc::tc_conv_kernel<TN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<TN, false>::SMEM);
     attr[h->device & 63] = true;
   }
-  const long long tiles = (long long)tp.n_tiles * tp.t_tiles * tp.B * (tp.nphase > 0 ? tp.nphase : 1);
+  tp.t_tiles = (tp.T + tc::BM - 1) / tc::BM;
+  const long long tiles = (long long)tp.n_tiles * tp.t_tiles * tp.B * nph;
   const int grid = (int)std::min<long long>(tiles, h->sm_count);
-  tc::tc_conv_kernel<TN><<<grid, tc::NUM_THREADS, tc::Cfg<TN>::SMEM, st>>>(tp);
+  tc::tc_conv_kernel<TN, false><<<grid, tc::NUM_THREADS, tc::Cfg<TN, false>::SMEM, st>>>(tp);
 }
 
 static void launch_tc_bn(cube_voc* h, int bn, tc::TcParams& tp, cudaStream_t st) {
@@ -1037,11 +1067,6 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
         ws_get(h, "c16", (size_t)B * T * CI, &t3)) return 1;
     h16 = (__half*)t1; o16 = (__half*)t2; c16 = (__half*)t3;
     if (make_tmap_hl16(&tm_h, h16, B, T, R) || make_tmap_hl16(&tm_o, o16, B, T, G) || make_tmap_hl16(&tm_c, c16, B, T, CI)) return 1;
-    static bool attr[64] = {false};
-    if (!attr[h->device & 63]) {
-      CU_TRY(cudaFuncSetAttribute(tc::tc_conv_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<256>::SMEM));
-      attr[h->device & 63] = true;
-    }
     lx.begin("to_hl16");
     tc::to_hl16_kernel<<<dim3((T + 31) / 32, (CI + 31) / 32, B), 256, 0, st>>>(cup, c16, B, CI, T);
     lx.check();
@@ -1050,12 +1075,10 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
   auto launch_tc = [&](const TcPacked& pk, tc::TcParams& tp) {
     tp.Wimg = pk.Wimg; tp.inv_scale = pk.inv_scale; tp.bias = pk.bias;
     tp.nseg = pk.nseg; tp.nchunks_total = pk.nchunks_total;
-    tp.B = B; tp.T = T; tp.n_tiles = pk.n_tiles; tp.t_tiles = (T + tc::BM - 1) / tc::BM;
+    tp.B = B; tp.T = T; tp.n_tiles = pk.n_tiles;
     tp.lens = lens_T;
-    const long long tiles = (long long)tp.n_tiles * tp.t_tiles * B;
-    const int grid = (int)std::min<long long>(tiles, h->sm_count);
     tp.nphase = 1; tp.a_inv_scale = 1.f; tp.plane_scale = 1.f;
-    tc::tc_conv_kernel<256><<<grid, tc::NUM_THREADS, tc::Cfg<256>::SMEM, st>>>(tp);
+    launch_tc_t<256>(h, tp, st);
     lx.check();
   };
   for (int f = 0; f < c.n_flows; ++f) {

@@ -46,9 +46,11 @@ __host__ __device__ constexpr int swz_off(int r, int k) {
 }
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BN * 8 /*scale,bias*/;
 // per-N-tile-width variants (HiFi-GAN stages have 256/128/64/32 output channels)
-template <int TN> struct Cfg {
+template <int TN, bool CG2 = false> struct Cfg {
   static_assert(TN == 256 || TN == 128 || TN == 64 || TN == 32, "tile N");
-  static constexpr int B_BYTES = TN * BK * 2;
+  // CG2: a CTA pair computes a 256-row x TN tile with tcgen05.mma.cta_group::2; each CTA stages its own
+  // 128 rows of A and HALF of the weight tile (the pair's tensor cores exchange the halves)
+  static constexpr int B_BYTES = (CG2 ? TN / 2 : TN) * BK * 2;
   static constexpr int STAGE = 2 * A_TILE_BYTES + 2 * B_BYTES;
   static constexpr int NSTAGE = (190 * 1024 / STAGE) > 8 ? 8 : (190 * 1024 / STAGE);
   static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256 + TN * 8;
@@ -182,6 +184,49 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- 2-CTA (cta_group::2) variants ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of the pair's MMAs -> one arrival on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -209,8 +254,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 }
 
 // instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, int m = BM) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ __half f2h_sat(float x) {
@@ -265,20 +310,25 @@ __device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int TN>
+template <int TN, bool CG2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcParams p) {
-  constexpr int STAGES = Cfg<TN>::NSTAGE;
-  constexpr int STAGE_BYTES = Cfg<TN>::STAGE;
-  constexpr int B_TILE_BYTES = Cfg<TN>::B_BYTES;
+  constexpr int STAGES = Cfg<TN, CG2>::NSTAGE;
+  constexpr int STAGE_BYTES = Cfg<TN, CG2>::STAGE;
+  constexpr int B_TILE_BYTES = Cfg<TN, CG2>::B_BYTES;
   constexpr int BN = TN;
+  constexpr int TILE_ROWS = CG2 ? 2 * BM : BM;     // rows of one scheduled tile (p.t_tiles counts these)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + STAGES;       // [STAGES]
-  uint64_t* tfull = bars + 2 * STAGES;   // [2]
-  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* pfull = bars + 2 * STAGES;   // [STAGES] (CG2, leader CTA): the peer CTA's stage is full
+  uint64_t* tfull = bars + 3 * STAGES;   // [2]
+  uint64_t* tempty = bars + 3 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+  const uint32_t crank = CG2 ? cluster_ctarank() : 0u;      // 0 = leader (issues the pair's MMAs)
+  const int tile0 = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   float2* s_sb = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 256);   // [BN] (inv_scale, bias) of this tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -288,13 +338,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA[0]);
     if (p.nseg > 1) prefetch_tmap(&p.tmA[1]);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], NUM_EPI_WARPS); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&pfull[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], CG2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg<TN>::TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (CG2) tmem_alloc2(tmem_slot, Cfg<TN, CG2>::TMEM_COLS); else tmem_alloc(tmem_slot, Cfg<TN, CG2>::TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG2) cluster_sync_all();     // both CTAs' barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -302,12 +355,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
     // =========================== TMA producer ===========================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int nt = tile % p.n_tiles;
         int rest = tile / p.n_tiles;
         const int ph = rest % nphase; rest /= nphase;
         const int tt = rest % p.t_tiles, b = rest / p.t_tiles;
-        const int t0 = tt * BM;
+        const int t0 = tt * TILE_ROWS + (int)crank * BM;
         const __half* wt = p.Wimg + (size_t)ph * p.w_phase_stride + (size_t)nt * p.nchunks_total * 2 * (BN * BK);
         int chunk = 0;
         for (int s = 0; s < p.nseg; ++s) {
@@ -322,7 +375,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
               mbar_expect_tx(&full[st], STAGE_BYTES);
               tma_load_3d(sb, &p.tmA[s], &full[st], cc * BK, row, b);
               tma_load_3d(sb + A_TILE_BYTES, &p.tmA[s], &full[st], cc * BK, row, p.B + b);
-              const __half* wc = wt + (size_t)chunk * 2 * (BN * BK);
+              // weight tile rows [crank*BN/2, +BN/2) when the pair splits it, else all BN rows
+              const __half* wc = wt + (size_t)chunk * 2 * (BN * BK) + (CG2 ? (size_t)crank * (BN / 2) * BK : 0);
               bulk_load(sb + 2 * A_TILE_BYTES, wc, B_TILE_BYTES, &full[st]);
               bulk_load(sb + 2 * A_TILE_BYTES + B_TILE_BYTES, wc + BN * BK, B_TILE_BYTES, &full[st]);
             }
@@ -333,39 +387,64 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TN);
-      uint32_t it = 0, titer = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
-        const uint32_t acc = titer & 1, aph = (titer >> 1) & 1;
-        mbar_wait(&tempty[acc], aph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        uint32_t accumulate = 0;
-        for (int s = 0; s < p.nseg; ++s) {
-          const TcSeg sg = p.seg[s];
-          for (int tap = 0; tap < sg.taps; ++tap) {
-            for (int cc = 0; cc < sg.nchunks; ++cc, ++it) {
+      if (CG2 && crank != 0) {
+        // peer CTA of a pair: it issues no MMA; this thread relays "my stage is full" to the leader
+        uint32_t it = 0;
+        for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+          for (int s = 0; s < p.nseg; ++s) {
+            const TcSeg sg = p.seg[s];
+            for (int n = sg.taps * sg.nchunks; n > 0; --n, ++it) {
               const int st = it % STAGES;
-              const uint32_t par = (it / STAGES) & 1;
-              mbar_wait(&full[st], par);
-              tc_fence_after();
-              const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES);
-              const uint32_t a_lo = a_hi + A_TILE_BYTES;
-              const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
-              const uint32_t b_lo = b_hi + B_TILE_BYTES;
-              const int ksteps = (cc == sg.nchunks - 1) ? sg.last_ksteps : (BK / 16);
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t ko = ks * 32;  // 16 fp16 = 32 bytes along K inside the swizzle span
-                umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
-                accumulate = 1;
-                umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
-                umma_f16(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
-              }
-              umma_commit(&empty[st]);   // frees the smem stage when these MMAs have read it
+              mbar_wait(&full[st], (it / STAGES) & 1);
+              mbar_arrive_remote(&pfull[st], 0);
             }
           }
         }
-        umma_commit(&tfull[acc]);        // accumulator complete -> epilogue
+      } else {
+        constexpr uint32_t idesc = make_idesc(TN, CG2 ? 2 * BM : BM);
+        uint32_t it = 0, titer = 0;
+        for (int tile = tile0; tile < total_tiles; tile += tile_step, ++titer) {
+          const uint32_t acc = titer & 1, aph = (titer >> 1) & 1;
+          mbar_wait(&tempty[acc], aph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          uint32_t accumulate = 0;
+          for (int s = 0; s < p.nseg; ++s) {
+            const TcSeg sg = p.seg[s];
+            for (int tap = 0; tap < sg.taps; ++tap) {
+              for (int cc = 0; cc < sg.nchunks; ++cc, ++it) {
+                const int st = it % STAGES;
+                const uint32_t par = (it / STAGES) & 1;
+                mbar_wait(&full[st], par);
+                if constexpr (CG2) mbar_wait(&pfull[st], par);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES);
+                const uint32_t a_lo = a_hi + A_TILE_BYTES;
+                const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
+                const uint32_t b_lo = b_hi + B_TILE_BYTES;
+                const int ksteps = (cc == sg.nchunks - 1) ? sg.last_ksteps : (BK / 16);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  const uint32_t ko = ks * 32;  // 16 fp16 = 32 bytes along K inside the swizzle span
+                  if constexpr (CG2) {
+                    umma_f16_2(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
+                    accumulate = 1;
+                    umma_f16_2(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+                    umma_f16_2(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                  } else {
+                    umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
+                    accumulate = 1;
+                    umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+                    umma_f16(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                  }
+                }
+                // frees the smem stage (in both CTAs of a pair) when these MMAs have read it
+                if constexpr (CG2) umma_commit_2(&empty[st]); else umma_commit(&empty[st]);
+              }
+            }
+          }
+          // accumulator complete -> epilogue (of both CTAs of a pair)
+          if constexpr (CG2) umma_commit_2(&tfull[acc]); else umma_commit(&tfull[acc]);
+        }
       }
     }
   } else {
@@ -376,12 +455,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
     const int row = q * 32 + lane;          // tile row = time step within the tile
     const int etid = threadIdx.x - 64;      // 0..511
     uint32_t titer = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++titer) {
       const int nt = tile % p.n_tiles;
       int rest = tile / p.n_tiles;
       const int ph = rest % nphase; rest /= nphase;
       const int tt = rest % p.t_tiles, b = rest / p.t_tiles;
-      const int t = tt * BM + row;
+      const int t = tt * TILE_ROWS + (int)crank * BM + row;
       const uint32_t acc = titer & 1, aph = (titer >> 1) & 1;
       // per-column (de-scale, bias) of this tile -> smem.  For the gate the exp2 pre-factors are
       // folded in: filter columns carry 2*log2(e) (-> 2^a = e^{2f}), gate columns -log2(e) (-> e^{-g}).
@@ -634,14 +713,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
       }  // TN == 256 (ClariNet epilogues)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (CG2 && crank != 0) mbar_arrive_remote(&tempty[acc], 0);   // the leader's MMA thread owns the accumulators' reuse
+        else mbar_arrive(&tempty[acc]);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG2) cluster_sync_all();     // no CTA of the pair exits while the other may still signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg<TN>::TMEM_COLS);
+    if constexpr (CG2) tmem_dealloc2(tmem_base, Cfg<TN, CG2>::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg<TN, CG2>::TMEM_COLS);
   }
 }
 
