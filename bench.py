@@ -32,6 +32,8 @@ WORKLOADS = {
     # name: (arch, batch per GPU, frames, description)
     "pwn": ("student", 8, 862, "BASELINE configs[1]: batch=8 x 10 s (F=862, T=220672), 80-bin synthetic mel, ParallelWaveNet student"),
     "hifigan": ("hifigan", 64, 919, "BASELINE configs[2]: batch=64 x 10 s (F=919), HiFi-GAN generator (neb-noft rates [3,5,4,4])"),
+    # configs[3]: 256 utterances of 2-15 s on rank 0, LPT-sharded over the ranks, NCCL scatter/gather (strong scaling)
+    "ragged": ("hifigan", 256, 0, "BASELINE configs[3]: batch=256 variable-length (2-15 s) utterances, HiFi-GAN generator, sharded across the ranks via NCCL p2p scatter/gather"),
 }
 # algorithmic work per output sample of the dominant kernel (DESIGN.md "Measurement")
 GATE_FLOPS = 2.0 * (2 * 256 * 128 * 3 + 2 * 256 * 80)     # gated dilated conv + conditioning 1x1
@@ -186,6 +188,78 @@ def run_reference(args, arch, B, F, desc, rank, world):
     print(json.dumps(line))
 
 
+def run_ragged(args, desc, rank, world, local):
+    """configs[3]: rank 0 owns 256 variable-length mels; tts_cube_b200.synthesize shards them (LPT), scatters the
+    padded mel blocks, every rank vocodes its shard, rank 0 gathers the audio.  Strong scaling: the work is fixed."""
+    import torch.distributed as dist
+    import tts_cube_b200 as cube
+    from oracle import hifigan_ref as H
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    weights, wdesc = load_weights("hifigan")
+    voc = cube.CubeGenerator(weights[1]).to(dev)
+    voc.load_state_dict(weights[0])
+    g = torch.Generator().manual_seed(1234 + 3)
+    n_utt = args.batch or 256
+    secs = torch.empty(n_utt).uniform_(2.0, 15.0, generator=g)
+    frames = [int(round(float(s_) * SR / 240)) for s_ in secs]
+    mels = None
+    if rank == 0:
+        big = H.synthetic_mel(1, max(frames) + 64 * 0, seed=77)[0]
+        mels = [torch.roll(big, shifts=37 * i, dims=1)[:, :f].contiguous().to(dev) for i, f in enumerate(frames)]
+    total = sum(voc.out_len(f) for f in frames)
+
+    def step():
+        with torch.no_grad():
+            return cube.synthesize(voc, mels, device=dev, max_batch=64, max_frames=64 * 1400)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step()
+        launches += voc._ensure().launches()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        assert all(o.numel() == voc.out_len(f) for o, f in zip(out, frames))
+        value = total * args.steps / (ms / 1e3)
+        plan = cube.lpt_shard(frames, world)
+        loads = [sum(frames[i] for i in p_) for p_ in plan]
+        print(json.dumps({
+            "metric": "audio samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic; " + wdesc, "rtf": value / SR,
+            "config": {"workload": desc, "utterances": n_utt, "total_seconds_of_audio": total / SR, "frames_min_max": [min(frames), max(frames)],
+                       "parallelism": f"dp{world}: LPT shards (max/mean load {max(loads) / (sum(loads) / world):.3f}), NCCL p2p scatter of mel / gather of audio",
+                       "l2": "per-step working set >> 126 MB L2"},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "device-resident lists in, device-resident lists out (rank 0); includes padding, scatter, gather"},
+            "gpu_launches": launches, "clocks": clocks, "lib": cube.build_info()}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -208,6 +282,9 @@ def main():
         run_reference(args, arch, B, F, desc, rank, world)
         return
     args.warmup = max(args.warmup, 3)
+    if args.workload == "ragged":
+        run_ragged(args, desc, rank, world, local)
+        return
 
     import torch.distributed as dist
     import tts_cube_b200 as cube

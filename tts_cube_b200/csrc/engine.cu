@@ -840,7 +840,8 @@ static void launch_tc_t(cube_voc* h, tc::TcParams& tp, cudaStream_t st) {
       cudaFuncSetAttribute(tc::tc_conv_kernel<TN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<TN, true>::SMEM);
       attr2[h->device & 63] = true;
     }
-    tp.t_tiles = (tp.T + 2 * tc::BM - 1) / (2 * tc::BM);
+    constexpr int rows2 = 2 * tc::BM * tc::Cfg<TN, true>::MSUB;
+    tp.t_tiles = (tp.T + rows2 - 1) / rows2;
     const long long tiles = (long long)tp.n_tiles * tp.t_tiles * tp.B * nph;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -860,7 +861,8 @@ static void launch_tc_t(cube_voc* h, tc::TcParams& tp, cudaStream_t st) {
     cudaFuncSetAttribute(tc::tc_conv_kernel<TN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<TN, false>::SMEM);
     attr[h->device & 63] = true;
   }
-  tp.t_tiles = (tp.T + tc::BM - 1) / tc::BM;
+  constexpr int rows1 = tc::BM * tc::Cfg<TN, false>::MSUB;
+  tp.t_tiles = (tp.T + rows1 - 1) / rows1;
   const long long tiles = (long long)tp.n_tiles * tp.t_tiles * tp.B * nph;
   const int grid = (int)std::min<long long>(tiles, h->sm_count);
   tc::tc_conv_kernel<TN, false><<<grid, tc::NUM_THREADS, tc::Cfg<TN, false>::SMEM, st>>>(tp);

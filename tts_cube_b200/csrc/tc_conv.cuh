@@ -51,10 +51,14 @@ template <int TN, bool CG2 = false> struct Cfg {
   // CG2: a CTA pair computes a 256-row x TN tile with tcgen05.mma.cta_group::2; each CTA stages its own
   // 128 rows of A and HALF of the weight tile (the pair's tensor cores exchange the halves)
   static constexpr int B_BYTES = (CG2 ? TN / 2 : TN) * BK * 2;
-  static constexpr int STAGE = 2 * A_TILE_BYTES + 2 * B_BYTES;
+  // narrow tiles are overhead-bound at 128 rows (a 128x32 tile is only 16 KB of output): a scheduled tile
+  // then covers MSUB 128-row sub-tiles that share the staged weight chunk, the barriers and the tile setup
+  static constexpr int MSUB = TN == 32 ? 4 : (TN == 64 ? 2 : 1);
+  static constexpr int A_BYTES = MSUB * A_TILE_BYTES;           // per plane
+  static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int NSTAGE = (190 * 1024 / STAGE) > 8 ? 8 : (190 * 1024 / STAGE);
   static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256 + TN * 8;
-  static constexpr int TMEM_COLS = (2 * TN < 32) ? 32 : 2 * TN;
+  static constexpr int TMEM_COLS = 2 * MSUB * TN;              // 256 or 512: double-buffered accumulators
 };
 constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
@@ -154,6 +158,7 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -316,7 +321,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
   constexpr int STAGE_BYTES = Cfg<TN, CG2>::STAGE;
   constexpr int B_TILE_BYTES = Cfg<TN, CG2>::B_BYTES;
   constexpr int BN = TN;
-  constexpr int TILE_ROWS = CG2 ? 2 * BM : BM;     // rows of one scheduled tile (p.t_tiles counts these)
+  constexpr int MSUB = Cfg<TN, CG2>::MSUB;
+  constexpr int A_BYTES = Cfg<TN, CG2>::A_BYTES;
+  constexpr int CTA_ROWS = MSUB * BM;               // rows this CTA owns in a scheduled tile
+  constexpr int TILE_ROWS = CG2 ? 2 * CTA_ROWS : CTA_ROWS;   // rows of one scheduled tile (p.t_tiles counts these)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -360,7 +368,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
         int rest = tile / p.n_tiles;
         const int ph = rest % nphase; rest /= nphase;
         const int tt = rest % p.t_tiles, b = rest / p.t_tiles;
-        const int t0 = tt * TILE_ROWS + (int)crank * BM;
+        const int t0 = tt * TILE_ROWS + (int)crank * CTA_ROWS;
         const __half* wt = p.Wimg + (size_t)ph * p.w_phase_stride + (size_t)nt * p.nchunks_total * 2 * (BN * BK);
         int chunk = 0;
         for (int s = 0; s < p.nseg; ++s) {
@@ -373,12 +381,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
               mbar_wait(&empty[st], par ^ 1);
               uint8_t* sb = smem + st * STAGE_BYTES;
               mbar_expect_tx(&full[st], STAGE_BYTES);
-              tma_load_3d(sb, &p.tmA[s], &full[st], cc * BK, row, b);
-              tma_load_3d(sb + A_TILE_BYTES, &p.tmA[s], &full[st], cc * BK, row, p.B + b);
+#pragma unroll
+              for (int ms = 0; ms < MSUB; ++ms) {
+                tma_load_3d(sb + ms * A_TILE_BYTES, &p.tmA[s], &full[st], cc * BK, row + ms * BM, b);
+                tma_load_3d(sb + A_BYTES + ms * A_TILE_BYTES, &p.tmA[s], &full[st], cc * BK, row + ms * BM, p.B + b);
+              }
               // weight tile rows [crank*BN/2, +BN/2) when the pair splits it, else all BN rows
               const __half* wc = wt + (size_t)chunk * 2 * (BN * BK) + (CG2 ? (size_t)crank * (BN / 2) * BK : 0);
-              bulk_load(sb + 2 * A_TILE_BYTES, wc, B_TILE_BYTES, &full[st]);
-              bulk_load(sb + 2 * A_TILE_BYTES + B_TILE_BYTES, wc + BN * BK, B_TILE_BYTES, &full[st]);
+              bulk_load(sb + 2 * A_BYTES, wc, B_TILE_BYTES, &full[st]);
+              bulk_load(sb + 2 * A_BYTES + B_TILE_BYTES, wc + BN * BK, B_TILE_BYTES, &full[st]);
             }
           }
         }
@@ -407,7 +418,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
           const uint32_t acc = titer & 1, aph = (titer >> 1) & 1;
           mbar_wait(&tempty[acc], aph ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * BN;
+          const uint32_t d_tmem = tmem_base + acc * (MSUB * BN);
           uint32_t accumulate = 0;
           for (int s = 0; s < p.nseg; ++s) {
             const TcSeg sg = p.seg[s];
@@ -418,24 +429,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
                 mbar_wait(&full[st], par);
                 if constexpr (CG2) mbar_wait(&pfull[st], par);
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES);
-                const uint32_t a_lo = a_hi + A_TILE_BYTES;
-                const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
+                const uint32_t a_hi0 = smem_u32(smem + st * STAGE_BYTES);
+                const uint32_t b_hi = a_hi0 + 2 * A_BYTES;
                 const uint32_t b_lo = b_hi + B_TILE_BYTES;
                 const int ksteps = (cc == sg.nchunks - 1) ? sg.last_ksteps : (BK / 16);
                 for (int ks = 0; ks < ksteps; ++ks) {
                   const uint32_t ko = ks * 32;  // 16 fp16 = 32 bytes along K inside the swizzle span
-                  if constexpr (CG2) {
-                    umma_f16_2(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
-                    accumulate = 1;
-                    umma_f16_2(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
-                    umma_f16_2(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
-                  } else {
-                    umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
-                    accumulate = 1;
-                    umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
-                    umma_f16(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+#pragma unroll
+                  for (int ms = 0; ms < MSUB; ++ms) {
+                    const uint32_t a_hi = a_hi0 + ms * A_TILE_BYTES, a_lo = a_hi + A_BYTES;
+                    const uint32_t d = d_tmem + ms * BN;
+                    if constexpr (CG2) {
+                      umma_f16_2(d, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
+                      umma_f16_2(d, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+                      umma_f16_2(d, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                    } else {
+                      umma_f16(d, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
+                      umma_f16(d, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+                      umma_f16(d, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                    }
                   }
+                  accumulate = 1;
                 }
                 // frees the smem stage (in both CTAs of a pair) when these MMAs have read it
                 if constexpr (CG2) umma_commit_2(&empty[st]); else umma_commit(&empty[st]);
@@ -451,7 +465,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
     // =========================== epilogue (warps 2..17) ===========================
     constexpr float LOG2E = 1.4426950408889634f;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int sub = (warp - 2) >> 2;        // 0..3: which quarter of the tile's work this warp owns
+    const int grp = (warp - 2) >> 2;        // 0..3: warp group (one warp per TMEM lane quarter each)
+    const int msub = grp % MSUB;            // 128-row sub-tile this warp reads
+    const int sub = grp / MSUB;             // which slice of that sub-tile's columns (4/MSUB slices)
     const int row = q * 32 + lane;          // tile row = time step within the tile
     const int etid = threadIdx.x - 64;      // 0..511
     uint32_t titer = 0;
@@ -460,7 +476,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
       int rest = tile / p.n_tiles;
       const int ph = rest % nphase; rest /= nphase;
       const int tt = rest % p.t_tiles, b = rest / p.t_tiles;
-      const int t = tt * TILE_ROWS + (int)crank * BM + row;
+      const int t = tt * TILE_ROWS + (int)crank * CTA_ROWS + msub * BM + row;
       const uint32_t acc = titer & 1, aph = (titer >> 1) & 1;
       // per-column (de-scale, bias) of this tile -> smem.  For the gate the exp2 pre-factors are
       // folded in: filter columns carry 2*log2(e) (-> 2^a = e^{2f}), gate columns -log2(e) (-> e^{-g}).
@@ -474,15 +490,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
         s_sb[etid] = make_float2(sc, bi);
       }
       asm volatile("bar.sync 1, 512;" ::: "memory");
-      mbar_wait(&tfull[acc], aph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + (acc * MSUB + msub) * BN + ((uint32_t)(q * 32) << 16);
       const int len = p.lens ? min(p.lens[b], p.T) : p.T;
       const bool in_range = t < p.T;
       const bool valid = t < len;
+      // The epilogue's GLOBAL operands (residual planes, skip accumulator) do not depend on the MMAs: pull
+      // them into L2 now, so that the loads issued after the accumulator wait pay L2 latency, not DRAM
+      // latency (a register prefetch of the same data spilled: 64 extra live registers at 96/thread).
+      if (in_range) {
+        if (p.epi == TC_EPI_CONV) {
+          if (p.res16) {
+            const int t_out = t * p.ostride + p.ooff[ph];
+            if (t_out >= 0 && t_out < p.L_out) {
+              const __half* r0 = p.res16 + ((size_t)b * p.L_out + t_out) * p.outC + nt * BN + sub * (BN * MSUB / 4);
+              prefetch_l2(r0);
+              prefetch_l2(r0 + (size_t)p.B * p.L_out * p.outC);
+            }
+          }
+        } else if (p.epi == TC_EPI_RESSKIP) {
+          if (sub < 2) {
+            const __half* h0 = p.h16 + ((size_t)b * p.T + t) * p.hC + sub * 64;   // 128 B per plane
+            prefetch_l2(h0);
+            prefetch_l2(h0 + (size_t)p.B * p.T * p.hC);
+          } else if (!p.skip_set && (lane & 7) == 0) {   // 8 floats = one 32 B sector per prefetch
+            const float* s0 = p.skip + ((size_t)b * (BN / 2) + (sub - 2) * 64) * p.T + t;
+#pragma unroll 8
+            for (int j = 0; j < 64; ++j) prefetch_l2(s0 + (size_t)j * p.T);
+          }
+        }
+      }
+      mbar_wait(&tfull[acc], aph);
+      tc_fence_after();
       if (p.epi == TC_EPI_CONV) {
         // ---- HiFi-GAN convolution epilogue: bias, residual, leaky-ReLU, ResBlock averaging ----
-        constexpr int CPS = BN / 4;                       // columns per epilogue sub-group
+        constexpr int CPS = BN * MSUB / 4;                // columns per epilogue warp
         constexpr int CW = CPS < 16 ? CPS : 16;           // columns per TMEM load
         const int t_out = t * p.ostride + p.ooff[ph];
         const int olen = p.lens ? min(p.lens[b], p.L_out) : p.L_out;
