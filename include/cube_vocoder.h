@@ -28,8 +28,11 @@ typedef void* cube_stream_t; /* cudaStream_t */
 
 enum cube_voc_arch {
   CUBE_VOC_HIFIGAN = 0,     /* hifigan/models.py:Generator (Path H)                               */
-  CUBE_VOC_PWN_STUDENT = 1  /* ClariNet IAF student + UpsampleNet2 (Path C), weights-only in ref  */
+  CUBE_VOC_PWN_STUDENT = 1, /* ClariNet IAF student + UpsampleNet2 (Path C), weights-only in ref  */
+  CUBE_VOC_WAVERNN = 2      /* cube/networks/modules.py:WaveRNN (Path W), autoregressive          */
 };
+
+enum cube_wavernn_head { CUBE_HEAD_MOL = 0, CUBE_HEAD_GM = 1, CUBE_HEAD_MULAW = 2, CUBE_HEAD_RAW = 3 };
 
 enum cube_voc_math {
   CUBE_MATH_FP32_SIMT = 0,  /* fp32 FFMA everywhere                                                */
@@ -66,6 +69,11 @@ typedef struct cube_voc_config {
   int32_t dilation_base, dilation_cycle;              /* 3, 6 : d_i = base^(i mod cycle) */
   int32_t n_upsample;
   int32_t upsample_scales[4];                         /* 16, 16 */
+  /* ---- WaveRNN (cube/networks/modules.py:393-446 constructor arguments) ---- */
+  int32_t wrnn_layers, wrnn_size;                     /* num_layers (1|2), layer_size */
+  int32_t wrnn_upsample, wrnn_upsample_low;           /* upsample, upsample_low */
+  int32_t wrnn_use_lowres;                            /* use_lowres */
+  int32_t wrnn_head;                                  /* enum cube_wavernn_head ('mol','gm','mulaw','raw') */
 } cube_voc_config;
 
 /* Generator(h) / Wavenet_Student(...) constructor.  device = CUDA ordinal. */
@@ -103,6 +111,20 @@ int cube_voc_forward(cube_voc_t* h, const float* mel, const int32_t* n_frames, c
  * Exactly one of wav / wav_i16 may be NULL. */
 int cube_voc_forward_host(cube_voc_t* h, const float* mel, const int32_t* n_frames, const float* noise,
                           float* wav, int16_t* wav_i16, int B, int64_t Fmax);
+
+/* WaveRNN._inference (cube/networks/modules.py:453-503): the autoregressive sample loop as one persistent
+ * cooperative kernel.  Handle created with arch = CUBE_VOC_WAVERNN; weights by the reference's state_dict keys
+ * ("_rnns.0.weight_ih_l0", "_lowres_conv.1.conv.weight", "_preoutput.linear_layer.bias", ...).
+ *   mel    device [B, F, 80]  (time-major, as WaveRNN takes it)
+ *   x_low  device [B, Tl] low-rate waveform, or NULL when use_lowres = 0
+ *   draws  device [T][B][K]: the sampling head's random numbers, K = nr_mix+1 uniforms in (1e-5, 1-1e-5)
+ *          (MOL: mixture pick then logistic), 1 normal (GM), or sample_size uniforms (MULAW/RAW, Gumbel-max)
+ *   x      device [B, T], T = cube_wavernn_out_len(h, F, Tl) = min(F*upsample, Tl*upsample_low)
+ * B is limited by shared memory (20 at layer_size 512); the Python layer splits larger batches. */
+int64_t cube_wavernn_out_len(const cube_voc_t* h, int64_t n_frames, int64_t n_low);
+int cube_wavernn_forward(cube_voc_t* h, const float* mel, const float* x_low, const float* draws, float* x,
+                         int B, int64_t F, int64_t Tl, cube_stream_t stream);
+int cube_wavernn_max_batch(const cube_voc_t* h);
 
 /* Debug/validation tap for Path C: upsampled conditioning c_up [B, 80, Tmax] of the last forward
  * (UpsampleNet2, cube/networks/modules.py:357-375).  Copies to a device buffer. */

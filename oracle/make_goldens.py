@@ -168,3 +168,42 @@ def write_mulaw_inc():
 
 if __name__ == "__main__":
     write_mulaw_inc()
+
+
+def wavernn_goldens():
+    """tests/golden/wavernn_{mol,gm}.npz: the reference WaveRNN (cube/networks/modules.py:392-503) with seeded
+    weights (stored) and torch.manual_seed; the head's per-step draws are replayed from the same seed."""
+    import contextlib, io
+    sys.path.insert(0, REF)
+    from cube.networks import modules as ref_mod
+    from oracle import wavernn_ref as R
+    for out, S in (("mol", 30), ("gm", 2)):
+        H_, up, upl, B, Fr = 32, 6, 3, 2, 4
+        m = ref_mod.WaveRNN(num_layers=2, layer_size=H_, upsample=up, upsample_low=upl, use_lowres=True, output=out).eval()
+        sd = R.random_state_dict(H_, 2, True, S, seed=31)
+        m.load_state_dict(sd, strict=True)
+        g = torch.Generator().manual_seed(17)
+        mel = torch.rand(B, Fr, 80, generator=g)
+        x_low = torch.rand(B, Fr * up // upl, generator=g) * 1.6 - 0.8
+        T = Fr * up
+        torch.manual_seed(123)
+        with contextlib.redirect_stderr(io.StringIO()):
+            y = m({"mel": mel, "x_low": x_low})
+        torch.manual_seed(123)
+        draws = {}
+        if out == "mol":
+            um, ux = [], []
+            for _ in range(T):
+                um.append(torch.empty(B, 1, 10).uniform_(1e-5, 1 - 1e-5)[:, 0])
+                ux.append(torch.empty(B, 1).uniform_(1e-5, 1.0 - 1e-5)[:, 0])
+            draws = {"u_mix": torch.stack(um), "u_x": torch.stack(ux)}
+        else:
+            draws = {"eps": torch.stack([torch.randn(B, 1, 1)[:, 0, 0] for _ in range(T)])}
+        np.savez_compressed(os.path.join(OUT, f"wavernn_{out}.npz"), mel=mel.numpy(), x_low=x_low.numpy(),
+                            x=np.asarray(y).reshape(B, T), upsample=up, upsample_low=upl,
+                            **{"d:" + k: v.numpy() for k, v in draws.items()}, **{"w:" + k: v.numpy() for k, v in sd.items()})
+        print("wavernn", out, np.asarray(y).shape, float(np.abs(y).max()))
+
+
+if __name__ == "__main__" and ("--wavernn" in sys.argv or "--inc-only" not in sys.argv):
+    wavernn_goldens()

@@ -319,3 +319,79 @@ def test_raw_mol_gaussian_categorical(dev):
     # sample() = decode(categorical): values come from the 256-entry table
     s = cube.MULAWOutput().sample(logits.to(dev), u.to(dev)).cpu()
     assert torch.equal(s[ok], W.mulaw_decode(ref)[ok])
+
+
+# ------------------------------------------------ Path W4 / W5 ------------------------------------------------
+@pytest.mark.parametrize("head", ["mol", "gm"])
+def test_wavernn_golden(dev, head):
+    """The persistent WaveRNN kernel replays the reference WaveRNN sample for sample (seeded weights and draws)."""
+    import tts_cube_b200 as cube
+    d = load_golden(f"wavernn_{head}.npz")
+    sd = golden_weights(d)
+    v = cube.WaveRNNVocoder(num_layers=2, layer_size=32, upsample=int(d["upsample"]), upsample_low=int(d["upsample_low"]),
+                            use_lowres=True, output=head).to(dev)
+    v.load_state_dict(sd)
+    if head == "mol":
+        draws = torch.cat([torch.from_numpy(d["d:u_mix"]), torch.from_numpy(d["d:u_x"]).unsqueeze(2)], dim=2)
+    else:
+        draws = torch.from_numpy(d["d:eps"]).unsqueeze(2)
+    x = v.inference(torch.from_numpy(d["mel"]).to(dev), torch.from_numpy(d["x_low"]).to(dev), draws.to(dev)).cpu().numpy()
+    err = float(np.abs(x - d["x"]).max())
+    print(f"wavernn {head}: max-abs {err:.3e}")
+    assert x.shape == d["x"].shape and err <= 1e-4
+    y = v({"mel": torch.from_numpy(d["mel"]), "x_low": torch.from_numpy(d["x_low"])}, draws=draws)
+    assert y.shape == d["x"].shape + (1,) and y.dtype == np.float32
+
+
+@pytest.mark.parametrize("head,H,L,lowres", [("mol", 512, 2, True), ("mulaw", 128, 1, False), ("raw", 64, 2, True), ("gm", 512, 2, False)])
+def test_wavernn_vs_oracle(dev, head, H, L, lowres):
+    """Full-size geometry (2 x 512 GRU, 20 folded chunks) and the categorical heads against the CPU oracle."""
+    import tts_cube_b200 as cube
+    from oracle import wavernn_ref as R
+    S = {"mol": 30, "gm": 2, "mulaw": 256, "raw": 256}[head]
+    sd = R.random_state_dict(H, L, lowres, S, seed=5)
+    up, upl, B, Fr = 10, 5, 20, 3
+    g = torch.Generator().manual_seed(3)
+    mel = torch.rand(B, Fr, 80, generator=g)
+    x_low = (torch.rand(B, Fr * up // upl, generator=g) * 1.6 - 0.8) if lowres else None
+    T = Fr * up
+    v = cube.WaveRNNVocoder(num_layers=L, layer_size=H, upsample=up, upsample_low=upl, use_lowres=lowres, output=head).to(dev)
+    v.load_state_dict(sd)
+    K = v.draws_shape(B, T)[2]
+    draws = torch.randn(T, B, K, generator=g) if head == "gm" else torch.empty(T, B, K).uniform_(1e-5, 1 - 1e-5, generator=g)
+    if head == "mol":
+        od = {"u_mix": draws[:, :, :10], "u_x": draws[:, :, 10]}
+    elif head == "gm":
+        od = {"eps": draws[:, :, 0]}
+    else:
+        od = {"u": draws}
+    ref = R.wavernn_inference(sd, mel, x_low, up, upl, head, od)
+    x = v.inference(mel.to(dev), x_low.to(dev) if lowres else None, draws.to(dev)).cpu()
+    # an autoregressive sampler amplifies a flipped arg-max; rows whose trajectories agree must agree closely,
+    # and (seeded) at least 90 % of them do
+    rowerr = (x - ref).abs().amax(dim=1)
+    good = rowerr <= 2e-3
+    print(f"wavernn {head} H={H}: rows ok {int(good.sum())}/{B}, max-abs over ok rows {float(rowerr[good].max()):.3e}")
+    assert float(good.float().mean()) >= 0.9
+
+
+def test_cubenet_vocoder_fold(dev):
+    """W5: fold/unfold equals the reference's numpy version; CubenetVocoder runs lr -> fold -> hr -> unfold."""
+    import tts_cube_b200 as cube
+    from tts_cube_b200.wavernn import fold_batch, unfold_batch
+    from oracle import wavernn_ref as R
+    mel = torch.rand(1, 43, 80)
+    xl = torch.rand(1, 430)
+    m, x = fold_batch(mel, xl, 10, 20)
+    mr, xr = R.fold_batch(mel, xl, 10, 20)
+    assert torch.equal(m, mr) and torch.equal(x, xr)
+    y = torch.rand(20, 300)
+    assert torch.equal(unfold_batch(y, 100), R.unfold_batch(y, 100))
+    voc = cube.CubenetVocoder(2, 64, 2, 64, upsample=20, upsample_low=4, output="mol").to(dev)
+    sd = {}
+    sd.update({"_wavernn_hr." + k: v for k, v in R.random_state_dict(64, 2, True, 30, seed=1).items()})
+    sd.update({"_wavernn_lr." + k: v for k, v in R.random_state_dict(64, 2, False, 30, seed=2).items()})
+    voc.load_state_dict(sd)
+    x_lr, x_hr = voc({"mel": torch.rand(1, 40, 80)})
+    assert x_lr.shape == (1, 40 * 5, 1) and x_hr.shape == (1, 20 * 2 * 20)
+    assert np.isfinite(x_lr).all() and bool(torch.isfinite(x_hr).all())

@@ -29,7 +29,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_config_struct_matches_header_size():
     from tts_cube_b200 import _lib
     # 3 + 2 + 8 + 8 + 2 + 8 + 8 + 64 + 1 + 8 + 3 + 2 + 2 + 1 + 4 int32 fields
-    assert ctypes.sizeof(_lib.VocConfig) == 4 * (3 + 2 + 16 + 2 + 16 + 64 + 1 + 8 + 3 + 2 + 2 + 1 + 4)
+    assert ctypes.sizeof(_lib.VocConfig) == 4 * (3 + 2 + 16 + 2 + 16 + 64 + 1 + 8 + 3 + 2 + 2 + 1 + 4 + 6)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")

@@ -109,3 +109,30 @@ def test_clarinet_self_consistency_probe(clarinet_weights):
     assert nll["3^n"] < nll["2^n"] - 0.3, nll
     assert nll["3^n"] < nll["3^n,noscale"] - 3.0, nll
     assert nll["3^n"] < -1.0, nll
+
+
+@pytest.mark.parametrize("head", ["mol", "gm"])
+def test_wavernn_oracle_matches_reference(head):
+    """Path W4: the restatement replays the reference WaveRNN (seeded weights, seeded draws) sample for sample."""
+    from oracle import wavernn_ref as R
+    d = load_golden(f"wavernn_{head}.npz")
+    sd = golden_weights(d)
+    draws = {k[2:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("d:")}
+    x = R.wavernn_inference(sd, torch.from_numpy(d["mel"]), torch.from_numpy(d["x_low"]), int(d["upsample"]),
+                            int(d["upsample_low"]), head, draws)
+    assert x.shape == d["x"].shape
+    assert float(np.abs(x.numpy() - d["x"]).max()) <= 2e-6
+    assert float(np.abs(d["x"]).max()) > 0.2
+
+
+def test_wavernn_fold_unfold():
+    """Path W5 (cube/networks/vocoder.py:109-131): fold one utterance into chunks with left context and back."""
+    from oracle import wavernn_ref as R
+    mel = torch.arange(1 * 43 * 80, dtype=torch.float).reshape(1, 43, 80)
+    xl = torch.arange(430, dtype=torch.float).reshape(1, 430)
+    m, x = R.fold_batch(mel, xl, upsample_low=10, num_batches=20)
+    assert m.shape == (20, 3, 80) and x.shape == (20, 31)
+    assert float(m[0, 0, 0]) == -5.0 and torch.equal(m[1, 0], mel[0, 1]) and torch.equal(m[3, 1:], mel[0, 6:8])
+    assert float(x[0, :10].abs().max()) == 0.0 and torch.equal(x[1, :10], xl[0, 11:21])
+    y = torch.arange(20 * 300, dtype=torch.float).reshape(20, 300)
+    assert R.unfold_batch(y, 100).shape == (1, 20 * 200)

@@ -3,6 +3,7 @@
 Host side mirrors the reference's interfaces for this path:
   ``CubeGenerator``            drop-in for ``hifigan.models.Generator`` (hifigan/models.py:72-125)
   ``ParallelWaveNetVocoder``   ClariNet IAF student + UpsampleNet2 (weights shipped by the reference)
+  ``WaveRNNVocoder`` / ``CubenetVocoder``  autoregressive WaveRNN path (cube/networks/modules.py:392-503, vocoder.py)
   ``MULAWOutput`` ...          output heads of ``cube/networks/loss.py``
   ``synthesize``               batch entry (mel list -> audio), sharded over ranks under torchrun
 All compute happens in libcube_vocoder.so (C ABI in include/cube_vocoder.h).
@@ -11,6 +12,7 @@ from ._lib import CubeVocError, build_info, LIB_PATH  # noqa: F401
 from .generator import CubeGenerator, install_into_cubegan  # noqa: F401
 from .clarinet import ParallelWaveNetVocoder  # noqa: F401
 from .heads import MULAWOutput, RAWOutput, MOLOutput, GaussianOutput  # noqa: F401
+from .wavernn import WaveRNNVocoder, CubenetVocoder  # noqa: F401
 from .api import synthesize, lpt_shard  # noqa: F401
 
 __version__ = "0.1.0"

@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcube_vocoder.so")
 
 MAX_UPS, MAX_RBK, MAX_DIL, MAX_FLOWS = 8, 8, 8, 8
-ARCH_HIFIGAN, ARCH_PWN_STUDENT = 0, 1
+ARCH_HIFIGAN, ARCH_PWN_STUDENT, ARCH_WAVERNN = 0, 1, 2
+HEADS = {"mol": 0, "gm": 1, "mulaw": 2, "raw": 3}
 MATH_FP32_SIMT, MATH_TC_SPLIT16 = 0, 1
 
 
@@ -30,6 +31,8 @@ class VocConfig(C.Structure):
         ("kernel_size", C.c_int32), ("front_kernel", C.c_int32),
         ("dilation_base", C.c_int32), ("dilation_cycle", C.c_int32),
         ("n_upsample", C.c_int32), ("upsample_scales", C.c_int32 * 4),
+        ("wrnn_layers", C.c_int32), ("wrnn_size", C.c_int32), ("wrnn_upsample", C.c_int32),
+        ("wrnn_upsample_low", C.c_int32), ("wrnn_use_lowres", C.c_int32), ("wrnn_head", C.c_int32),
     ]
 
 
@@ -49,6 +52,9 @@ SYMBOLS = {
     "cube_voc_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int64, _P]),
     "cube_voc_forward_host": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int64]),
     "cube_voc_get_cond": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P]),
+    "cube_wavernn_out_len": (C.c_int64, [_P, C.c_int64, C.c_int64]),
+    "cube_wavernn_forward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int64, C.c_int64, _P]),
+    "cube_wavernn_max_batch": (C.c_int, [_P]),
     "cube_voc_last_launches": (C.c_int64, [_P]),
     "cube_voc_workspace_bytes": (C.c_int64, [_P]),
     "cube_voc_set_profile": (C.c_int, [_P, C.c_int]),

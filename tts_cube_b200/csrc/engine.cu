@@ -17,6 +17,7 @@
 #include "conv_simt.cuh"
 #include "heads.cuh"
 #include "tc_conv.cuh"
+#include "wavernn.cuh"
 
 #define CUBE_VERSION "0.1.0"
 
@@ -116,6 +117,13 @@ struct cube_voc {
   std::vector<Flow> flows;
   struct Up2 { float w[192]; float bias; int s; };
   std::vector<Up2> up2;
+  // WaveRNN (Path W)
+  struct Wrnn {
+    PackedConv lowres[3], gx;
+    float *w_last = nullptr, *whh1 = nullptr, *bhh1 = nullptr, *wih2 = nullptr, *bih2 = nullptr, *whh2 = nullptr, *bhh2 = nullptr;
+    float *wpre = nullptr, *bpre = nullptr, *wout = nullptr, *bout = nullptr;
+    int S = 0, ic = 0;
+  } wr;
   // last-forward geometry (for get_cond)
   int last_B = 0; int64_t last_T = 0;
 };
@@ -1201,6 +1209,152 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
   return lx.err;
 }
 
+// ------------------------------------------------------------------------------------------------
+// WaveRNN (Path W): finalize + forward
+// ------------------------------------------------------------------------------------------------
+static int get_tensor(cube_voc* h, const std::string& name, std::initializer_list<int64_t> shape, const HostTensor** out) {
+  auto it = h->host_w.find(name);
+  if (it == h->host_w.end()) return fail("missing '%s'", name.c_str());
+  if (expect_shape(name, it->second, shape)) return 1;
+  *out = &it->second;
+  return 0;
+}
+
+static int wrnn_head_size(int head) { return head == CUBE_HEAD_MOL ? 30 : (head == CUBE_HEAD_GM ? 2 : 256); }
+
+static int finalize_wavernn(cube_voc* h) {
+  const cube_voc_config& c = h->cfg;
+  const int H = c.wrnn_size, L = c.wrnn_layers, nm = c.num_mels;
+  const int ic = nm + 1 + (c.wrnn_use_lowres ? 21 : 0);
+  const int S = wrnn_head_size(c.wrnn_head);
+  h->wr.S = S; h->wr.ic = ic;
+  if (c.wrnn_use_lowres) {
+    int ci = 1;
+    for (int i = 0; i < 3; ++i) {
+      if (pack_conv1d(h, "_lowres_conv." + std::to_string(i) + ".conv", 20, ci, 7, &h->wr.lowres[i])) return 1;
+      ci = 20;
+    }
+  }
+  const HostTensor *wih, *whh, *bih, *bhh;
+  if (get_tensor(h, "_rnns.0.weight_ih_l0", {3 * H, ic}, &wih) || get_tensor(h, "_rnns.0.weight_hh_l0", {3 * H, H}, &whh) ||
+      get_tensor(h, "_rnns.0.bias_ih_l0", {3 * H}, &bih) || get_tensor(h, "_rnns.0.bias_hh_l0", {3 * H}, &bhh)) return 1;
+  {  // input product for the ic-1 conditioning channels as a 1x1 conv: packed [C][Mpad]
+    PackedConv& pc = h->wr.gx;
+    pc.M = 3 * H; pc.Mpad = round_up(3 * H, 128); pc.Ktot = ic - 1; pc.nphase = 1;
+    std::vector<float> P((size_t)pc.Ktot * pc.Mpad, 0.f), Bv(pc.Mpad, 0.f), wl(3 * H);
+    for (int m = 0; m < 3 * H; ++m) {
+      Bv[m] = bih->data[m];
+      for (int k = 0; k < ic - 1; ++k) P[(size_t)k * pc.Mpad + m] = wih->data[(size_t)m * ic + k];
+      wl[m] = wih->data[(size_t)m * ic + ic - 1];
+    }
+    if (dev_upload(h, P, &pc.W) || dev_upload(h, Bv, &pc.bias) || dev_upload(h, wl, &h->wr.w_last)) return 1;
+  }
+  if (dev_upload(h, whh->data, &h->wr.whh1) || dev_upload(h, bhh->data, &h->wr.bhh1)) return 1;
+  if (L == 2) {
+    const HostTensor *a, *b2, *c2, *d2;
+    if (get_tensor(h, "_rnns.1.weight_ih_l0", {3 * H, H}, &a) || get_tensor(h, "_rnns.1.weight_hh_l0", {3 * H, H}, &b2) ||
+        get_tensor(h, "_rnns.1.bias_ih_l0", {3 * H}, &c2) || get_tensor(h, "_rnns.1.bias_hh_l0", {3 * H}, &d2)) return 1;
+    if (dev_upload(h, a->data, &h->wr.wih2) || dev_upload(h, b2->data, &h->wr.whh2) || dev_upload(h, c2->data, &h->wr.bih2) ||
+        dev_upload(h, d2->data, &h->wr.bhh2)) return 1;
+  }
+  const HostTensor *wp, *bp, *wo, *bo;
+  if (get_tensor(h, "_preoutput.linear_layer.weight", {wrnn::PRE, H}, &wp) || get_tensor(h, "_preoutput.linear_layer.bias", {wrnn::PRE}, &bp) ||
+      get_tensor(h, "_output.linear_layer.weight", {S, wrnn::PRE}, &wo) || get_tensor(h, "_output.linear_layer.bias", {S}, &bo)) return 1;
+  if (dev_upload(h, wp->data, &h->wr.wpre) || dev_upload(h, bp->data, &h->wr.bpre) || dev_upload(h, wo->data, &h->wr.wout) ||
+      dev_upload(h, bo->data, &h->wr.bout)) return 1;
+  return 0;
+}
+
+struct WrnnGeom { int G, U, P, SO; size_t smem; };
+
+static WrnnGeom wrnn_geom(const cube_voc* h, int B) {
+  const cube_voc_config& c = h->cfg;
+  const int H = c.wrnn_size, L = c.wrnn_layers, S = h->wr.S;
+  WrnnGeom g;
+  g.U = (H + h->sm_count - 1) / h->sm_count;
+  g.G = (H + g.U - 1) / g.U;
+  g.P = (wrnn::PRE + g.G - 1) / g.G;
+  g.SO = S <= 32 ? S : (S + g.G - 1) / g.G;
+  size_t f = (size_t)3 * g.U * H + 6 * g.U;
+  if (L == 2) f += (size_t)6 * g.U * H + 6 * g.U;
+  f += (size_t)g.P * H + g.P + (size_t)g.SO * wrnn::PRE + g.SO;
+  f += (size_t)B * H * (L == 2 ? 2 : 1) + (size_t)B * wrnn::PRE + (size_t)B * std::max(S, 1) + B;
+  g.smem = f * sizeof(float) + 64;
+  return g;
+}
+
+static int forward_wavernn(cube_voc* h, const float* mel, const float* x_low, const float* draws, float* x, int B, int64_t F,
+                           int64_t Tl, cudaStream_t st) {
+  const cube_voc_config& c = h->cfg;
+  const int H = c.wrnn_size, L = c.wrnn_layers, S = h->wr.S, nm = c.num_mels, ic = h->wr.ic;
+  if (c.wrnn_use_lowres && !x_low) return fail("x_low is required when use_lowres = 1");
+  int64_t T64 = F * c.wrnn_upsample;
+  if (c.wrnn_use_lowres) T64 = std::min<int64_t>(T64, Tl * c.wrnn_upsample_low);
+  if (T64 < 1 || T64 > 0x3fffffff) return fail("bad length");
+  const int T = (int)T64;
+  const WrnnGeom g = wrnn_geom(h, B);
+  if (g.smem > 227 * 1024) return fail("batch %d needs %zu B of shared memory per CTA (max 232448): split it (cube_wavernn_max_batch)", B, g.smem);
+  Launcher lx{h, st};
+  float *lowA = nullptr, *lowB = nullptr, *cond, *gx, *hbuf, *prebuf, *logits;
+  const int C = ic - 1;
+  if (ws_get(h, "w_cond", (size_t)B * C * T, &cond) || ws_get(h, "w_gx", (size_t)B * 3 * H * T, &gx) ||
+      ws_get(h, "w_h", (size_t)2 * L * B * H, &hbuf) || ws_get(h, "w_pre", (size_t)B * wrnn::PRE, &prebuf) ||
+      ws_get(h, "w_lg", (size_t)B * std::max(S, 1), &logits)) return 1;
+  if (c.wrnn_use_lowres) {
+    if (ws_get(h, "w_lowA", (size_t)B * 20 * Tl, &lowA) || ws_get(h, "w_lowB", (size_t)B * 20 * Tl, &lowB)) return 1;
+    // hidden = tanh(conv_k7(hidden)) x3 on the low-rate waveform (cube/networks/modules.py:459-461)
+    const float* src = x_low; int ci = 1; float* dst = lowA;
+    for (int i = 0; i < 3; ++i) {
+      lx.begin("wrnn_lowres");
+      ConvP p = make_conv(h->wr.lowres[i]);
+      p.nseg = 1;
+      p.seg[0] = make_seg(src, (long long)ci * Tl, ci, (int)Tl, 7, 1, -3, PRE_NONE, 0.f);
+      p.Q = (int)Tl; p.L_out = (int)Tl; p.post = POST_TANH;
+      p.out = dst; p.out_bstride = (long long)20 * Tl;
+      lx.conv(p, B);
+      lx.end();
+      src = dst; dst = (dst == lowA) ? lowB : lowA; ci = 20;
+    }
+    lowA = const_cast<float*>(src);   // final features
+  }
+  {
+    lx.begin("wrnn_cond");
+    wrnn::wavernn_cond_kernel<<<dim3((T + 255) / 256, C, B), 256, 0, st>>>(mel, lowA, x_low, cond, B, (int)F, nm, (int)std::max<int64_t>(Tl, 1),
+                                                                              c.wrnn_upsample, std::max(1, c.wrnn_upsample_low), T, C);
+    lx.check();
+    lx.end();
+  }
+  {  // gx[b][3H][t] = W_ih1[:, :ic-1] . cond[b][:, t] + b_ih1
+    lx.begin("wrnn_gx");
+    ConvP p = make_conv(h->wr.gx);
+    p.nseg = 1;
+    p.seg[0] = make_seg(cond, (long long)C * T, C, T, 1, 1, 0, PRE_NONE, 0.f);
+    p.Q = T; p.L_out = T; p.out = gx; p.out_bstride = (long long)3 * H * T;
+    lx.conv(p, B);
+    lx.end();
+  }
+  CU_TRY(cudaMemsetAsync(hbuf, 0, (size_t)2 * L * B * H * sizeof(float), st));
+  lx.begin("wrnn_loop");
+  wrnn::WrnnParams wp;
+  memset(&wp, 0, sizeof(wp));
+  wp.H = H; wp.L = L; wp.B = B; wp.T = T; wp.S = S; wp.head = c.wrnn_head; wp.U = g.U; wp.P = g.P;
+  wp.gx = gx; wp.w_last = h->wr.w_last; wp.whh1 = h->wr.whh1; wp.bhh1 = h->wr.bhh1;
+  wp.wih2 = h->wr.wih2; wp.bih2 = h->wr.bih2; wp.whh2 = h->wr.whh2; wp.bhh2 = h->wr.bhh2;
+  wp.wpre = h->wr.wpre; wp.bpre = h->wr.bpre; wp.wout = h->wr.wout; wp.bout = h->wr.bout;
+  wp.hbuf = hbuf; wp.prebuf = prebuf; wp.logits = logits; wp.draws = draws; wp.x_out = x;
+  wp.log_scale_min = logf(1e-14f);
+  static bool attr[64] = {false};
+  if (!attr[h->device & 63]) {
+    CU_TRY(cudaFuncSetAttribute(wrnn::wavernn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr[h->device & 63] = true;
+  }
+  void* args[] = {&wp};
+  CU_TRY(cudaLaunchCooperativeKernel((void*)wrnn::wavernn_kernel, dim3(g.G), dim3(wrnn::THREADS), args, g.smem, st));
+  h->launches++;
+  lx.end();
+  return lx.err;
+}
+
 static int ensure_device(cube_voc* h) {
   CU_TRY(cudaSetDevice(h->device));
   return 0;
@@ -1255,7 +1409,8 @@ int cube_voc_create(cube_voc_t** out, const cube_voc_config* cfg, int device) {
   if (e != cudaSuccess || ndev == 0)
     return fail("no CUDA device: libcube_vocoder has no CPU path (%s)", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
   if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
-  if (cfg->arch != CUBE_VOC_HIFIGAN && cfg->arch != CUBE_VOC_PWN_STUDENT) return fail("unknown arch %d", cfg->arch);
+  if (cfg->arch != CUBE_VOC_HIFIGAN && cfg->arch != CUBE_VOC_PWN_STUDENT && cfg->arch != CUBE_VOC_WAVERNN)
+    return fail("unknown arch %d", cfg->arch);
   if (cfg->arch == CUBE_VOC_HIFIGAN) {
     if (cfg->n_ups < 1 || cfg->n_ups > CUBE_MAX_UPS) return fail("n_ups %d out of range", cfg->n_ups);
     if (cfg->n_resblock_kernels < 1 || cfg->n_resblock_kernels > CUBE_MAX_RBK) return fail("n_resblock_kernels out of range");
@@ -1269,6 +1424,11 @@ int cube_voc_create(cube_voc_t** out, const cube_voc_config* cfg, int device) {
       if (cfg->resblock_kernel_sizes[j] % 2 != 1) return fail("resblock kernel sizes must be odd");
       if (cfg->n_dilations[j] < 1 || cfg->n_dilations[j] > CUBE_MAX_DIL) return fail("n_dilations out of range");
     }
+  } else if (cfg->arch == CUBE_VOC_WAVERNN) {
+    if (cfg->wrnn_layers < 1 || cfg->wrnn_layers > 2) return fail("WaveRNN num_layers must be 1 or 2");
+    if (cfg->wrnn_size < 8 || cfg->wrnn_size > 1024 || cfg->wrnn_size % 4) return fail("WaveRNN layer_size must be a multiple of 4 in [8, 1024]");
+    if (cfg->wrnn_upsample < 1 || (cfg->wrnn_use_lowres && cfg->wrnn_upsample_low < 1)) return fail("bad upsample");
+    if (cfg->wrnn_head < 0 || cfg->wrnn_head > 3) return fail("unknown head");
   } else {
     if (cfg->n_flows < 1 || cfg->n_flows > CUBE_MAX_FLOWS) return fail("n_flows out of range");
     if (cfg->n_upsample < 1 || cfg->n_upsample > 4) return fail("n_upsample out of range");
@@ -1307,7 +1467,7 @@ int cube_voc_finalize(cube_voc_t* h) {
   if (h->finalized) return 0;
   if (ensure_device(h)) return 1;
   if (tables_ready()) return 1;
-  int rc = h->cfg.arch == CUBE_VOC_HIFIGAN ? finalize_hifigan(h) : finalize_student(h);
+  int rc = h->cfg.arch == CUBE_VOC_HIFIGAN ? finalize_hifigan(h) : (h->cfg.arch == CUBE_VOC_WAVERNN ? finalize_wavernn(h) : finalize_student(h));
   if (rc) return rc;
   h->host_w.clear();
   CU_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -1334,6 +1494,7 @@ int cube_voc_forward(cube_voc_t* h, const float* mel, const int32_t* n_frames, c
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   h->prof.clear();
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->cfg.arch == CUBE_VOC_WAVERNN) return fail("use cube_wavernn_forward for a WaveRNN handle");
   if (h->cfg.arch == CUBE_VOC_HIFIGAN) return forward_hifigan(h, mel, n_frames, wav, wav_i16, B, Fmax, st);
   return forward_student(h, mel, n_frames, noise, wav, wav_i16, B, Fmax, st);
 }
@@ -1361,6 +1522,34 @@ int cube_voc_forward_host(cube_voc_t* h, const float* mel, const int32_t* n_fram
   if (wav_i16) CU_TRY(cudaMemcpyAsync(wav_i16, h->d_wav16, wav_n * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
   return 0;
+}
+
+int64_t cube_wavernn_out_len(const cube_voc_t* h, int64_t n_frames, int64_t n_low) {
+  if (!h || h->cfg.arch != CUBE_VOC_WAVERNN || n_frames < 0) { fail("bad argument"); return -1; }
+  int64_t T = n_frames * h->cfg.wrnn_upsample;
+  if (h->cfg.wrnn_use_lowres) T = std::min<int64_t>(T, n_low * h->cfg.wrnn_upsample_low);
+  return T;
+}
+
+int cube_wavernn_max_batch(const cube_voc_t* h) {
+  if (!h || h->cfg.arch != CUBE_VOC_WAVERNN || !h->finalized) { fail("bad handle"); return -1; }
+  int b = 1;
+  while (b < 1024 && wrnn_geom(h, b + 1).smem <= 227 * 1024) ++b;
+  return b;
+}
+
+int cube_wavernn_forward(cube_voc_t* h, const float* mel, const float* x_low, const float* draws, float* x, int B, int64_t F,
+                         int64_t Tl, cube_stream_t stream) {
+  if (!h) return fail("null handle");
+  if (h->cfg.arch != CUBE_VOC_WAVERNN) return fail("not a WaveRNN handle");
+  if (!h->finalized) return fail("forward before finalize");
+  if (!mel || !draws || !x) return fail("null argument");
+  if (B < 1 || F < 1) return fail("empty batch");
+  if (ensure_device(h)) return 1;
+  h->launches = 0;
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  h->prof.clear();
+  return forward_wavernn(h, mel, x_low, draws, x, B, F, Tl, (cudaStream_t)stream);
 }
 
 int cube_voc_get_cond(cube_voc_t* h, float* c_up, int B, int64_t Tmax, cube_stream_t stream) {
