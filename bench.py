@@ -383,7 +383,11 @@ def main():
         roof = {"kernel": "conv_tile_kernel<8,8,8,1> EPI_GATE (gated dilated conv k3 128->2x256 + conditioning 1x1 80->2x256, fp32 FFMA2)" if math == 0
                 else "tc::tc_conv_kernel TC_EPI_GATE (same layer on tcgen05: UMMA 128x256x16 f16, split-fp16 x3, TMA taps)",
                 "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                "frac": (ach / pk["tf_sust"]) if ach else None, "traffic": None,
+                "frac": (ach / pk["tf_sust"]) if ach else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, round 1
+                # (profiles/r1_ncu_full_tc_conv.md: 1.52 GB + 1.79 GB); only valid for the default geometry
+                "traffic": 3.31e9 if (math == 1 and B == 8 and F == 862) else None,
+                "traffic_source": "profiles/r1_ncu_full_tc_conv.md (ncu --set full, gate launch)",
                 "launches_per_step": nlaunch, "avg_launch_ms": dom_ms / max(1, nlaunch),
                 "algorithmic_flops_per_launch": flops_launch, "algorithmic_bytes_per_launch": GATE_BYTES * samples_per_step,
                 "share_of_step": dom_ms / (ms / args.steps) if ms > 0 else None,

@@ -393,5 +393,6 @@ def test_cubenet_vocoder_fold(dev):
     sd.update({"_wavernn_lr." + k: v for k, v in R.random_state_dict(64, 2, False, 30, seed=2).items()})
     voc.load_state_dict(sd)
     x_lr, x_hr = voc({"mel": torch.rand(1, 40, 80)})
-    assert x_lr.shape == (1, 40 * 5, 1) and x_hr.shape == (1, 20 * 2 * 20)
+    # hr chunk: 3 frames x 20 = 60 vs (10 + 4) low samples x 4 = 56 -> T = 56 (the reference's min()), minus the 20-sample context
+    assert x_lr.shape == (1, 40 * 5, 1) and x_hr.shape == (1, 20 * (56 - 20))
     assert np.isfinite(x_lr).all() and bool(torch.isfinite(x_hr).all())

@@ -269,13 +269,40 @@ __global__ void __launch_bounds__(256) conv_small_kernel(const SmallP p) {
   for (int c0 = 0; c0 < p.C; c0 += p.ci_chunk) {
     const int cn = min(p.ci_chunk, p.C - c0);
     __syncthreads();
+    // 128-bit loads when the rows allow it (HBM-bound layer: bytes in flight per thread matter): the window
+    // start is rounded down to a multiple of 4 samples and each lane moves one aligned float4 per step
+    const int wstart = q0 + p.off0;
+    const int astart = wstart & ~3;                         // floor to 4 (two's complement: fine for negatives)
+    const bool vec_ok = ((p.L & 3) == 0) && ((reinterpret_cast<uintptr_t>(srcb) & 15) == 0);
     for (int ci = tid >> 5; ci < cn; ci += 8) {
       const float* __restrict__ row = srcb + (long long)(c0 + ci) * p.L;
-      for (int sx = tid & 31; sx < XW; sx += 32) {
-        const int pos = q0 + p.off0 + sx;
-        float v = 0.f;
-        if (pos >= 0 && pos < p.L) v = apply_pre(__ldg(row + pos), p.preact, p.slope);
-        Xs[ci * XP + sx] = v;
+      if (vec_ok) {
+        const int nvec = (wstart + XW - astart + 3) >> 2;
+        for (int v4 = tid & 31; v4 < nvec; v4 += 32) {
+          const int pos = astart + 4 * v4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (pos >= 0 && pos + 3 < p.L) {
+            v = __ldg(reinterpret_cast<const float4*>(row + pos));
+          } else {
+            if (pos >= 0 && pos < p.L) v.x = __ldg(row + pos);
+            if (pos + 1 >= 0 && pos + 1 < p.L) v.y = __ldg(row + pos + 1);
+            if (pos + 2 >= 0 && pos + 2 < p.L) v.z = __ldg(row + pos + 2);
+            if (pos + 3 >= 0 && pos + 3 < p.L) v.w = __ldg(row + pos + 3);
+          }
+          const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int sx = pos + k - wstart;
+            if (sx >= 0 && sx < XW) Xs[ci * XP + sx] = apply_pre(e[k], p.preact, p.slope);
+          }
+        }
+      } else {
+        for (int sx = tid & 31; sx < XW; sx += 32) {
+          const int pos = wstart + sx;
+          float v = 0.f;
+          if (pos >= 0 && pos < p.L) v = apply_pre(__ldg(row + pos), p.preact, p.slope);
+          Xs[ci * XP + sx] = v;
+        }
       }
     }
     __syncthreads();

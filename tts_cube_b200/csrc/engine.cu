@@ -1265,7 +1265,7 @@ static int finalize_wavernn(cube_voc* h) {
   return 0;
 }
 
-struct WrnnGeom { int G, U, P, SO; size_t smem; };
+struct WrnnGeom { int G, U, P, SO, DG; size_t smem; };
 
 static WrnnGeom wrnn_geom(const cube_voc* h, int B) {
   const cube_voc_config& c = h->cfg;
@@ -1275,10 +1275,13 @@ static WrnnGeom wrnn_geom(const cube_voc* h, int B) {
   g.G = (H + g.U - 1) / g.U;
   g.P = (wrnn::PRE + g.G - 1) / g.G;
   g.SO = S <= 32 ? S : (S + g.G - 1) / g.G;
-  size_t f = (size_t)3 * g.U * H + 6 * g.U;
-  if (L == 2) f += (size_t)6 * g.U * H + 6 * g.U;
-  f += (size_t)g.P * H + g.P + (size_t)g.SO * wrnn::PRE + g.SO;
-  f += (size_t)B * H * (L == 2 ? 2 : 1) + (size_t)B * wrnn::PRE + (size_t)B * std::max(S, 1) + B;
+  using wrnn::al4;
+  g.DG = std::max(6 * g.U, std::max(g.P, S <= 32 ? 0 : g.SO));
+  size_t f = (size_t)3 * g.U * H + 2 * al4(3 * g.U);
+  if (L == 2) f += (size_t)6 * g.U * H + 2 * al4(3 * g.U);
+  f += (size_t)g.P * H + al4(g.P) + (size_t)g.SO * wrnn::PRE + al4(g.SO);
+  f += (size_t)al4(B * H) * (L == 2 ? 2 : 1) + al4(B * wrnn::PRE) + al4(B * std::max(S, 1)) + al4(B);
+  f += (size_t)al4(g.DG * B) + wrnn::THREADS;
   g.smem = f * sizeof(float) + 64;
   return g;
 }
@@ -1337,7 +1340,7 @@ static int forward_wavernn(cube_voc* h, const float* mel, const float* x_low, co
   lx.begin("wrnn_loop");
   wrnn::WrnnParams wp;
   memset(&wp, 0, sizeof(wp));
-  wp.H = H; wp.L = L; wp.B = B; wp.T = T; wp.S = S; wp.head = c.wrnn_head; wp.U = g.U; wp.P = g.P;
+  wp.H = H; wp.L = L; wp.B = B; wp.T = T; wp.S = S; wp.head = c.wrnn_head; wp.U = g.U; wp.P = g.P; wp.DG = g.DG;
   wp.gx = gx; wp.w_last = h->wr.w_last; wp.whh1 = h->wr.whh1; wp.bhh1 = h->wr.bhh1;
   wp.wih2 = h->wr.wih2; wp.bih2 = h->wr.bih2; wp.whh2 = h->wr.whh2; wp.bhh2 = h->wr.bhh2;
   wp.wpre = h->wr.wpre; wp.bpre = h->wr.bpre; wp.wout = h->wr.wout; wp.bout = h->wr.bout;

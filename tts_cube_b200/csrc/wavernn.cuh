@@ -26,6 +26,7 @@ constexpr int THREADS = 256;
 
 struct WrnnParams {
   int H, L, B, T, S, head, U, P;   // U = hidden units per CTA, P = pre-output rows per CTA
+  int DG;                          // rows of the dot-product scratch: max(6U, P, output rows per CTA)
   // weights (global; copied to smem once)
   const float* gx;                 // [B][3H][T]: W_ih1[:, :ic-1] . cond + b_ih1 for every step
   const float* w_last;             // [3H]      column of W_ih1 that multiplies the fed-back sample
@@ -44,6 +45,7 @@ struct WrnnParams {
   float log_scale_min;
 };
 
+__host__ __device__ constexpr int al4(int x) { return (x + 3) & ~3; }
 __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -52,15 +54,54 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// dot(w[0..n), x[0..n)) with the 32 lanes striding over n (both in shared memory)
-__device__ __forceinline__ float dot_ws(const float* w, const float* x, int n, int lane) {
-  float a = 0.f;
-  for (int k = lane; k < n; k += 32) a = fmaf(w[k], x[k], a);
-  return warp_sum(a);
-}
-
 __device__ __forceinline__ void copy_g2s(float* dst, const float* src, int n, int tid) {
   for (int i = tid; i < n; i += THREADS) dst[i] = src[i];
+}
+
+// global [B][K] -> shared, TRANSPOSED to [K][B]: in the dot products below consecutive lanes are consecutive batch
+// items, so they read consecutive shared-memory words while the weight element is a warp broadcast
+__device__ __forceinline__ void copy_g2s_T(float* dst, const float* src, int B, int K, int tid) {
+  for (int b = 0; b < B; ++b)
+    for (int k = tid; k < K; k += THREADS) dst[k * B + b] = src[b * K + k];   // coalesced reads, no division
+}
+
+// out[r*B + b] = dot(W[r][0..K), x[b][0..K)) for r < nrows, b < B; W row-major in smem, xT = [K][B] in smem.
+// One thread per (row, batch item) - no shuffles; when there are fewer than 256 such pairs the K range is split over
+// KS thread groups and the partial sums are combined through `part` (KS*nrows*B floats).
+__device__ __forceinline__ void dots(const float* W, int nrows, const float* xT, int B, int K, float* out, float* part, int tid) {
+  const int ntask = nrows * B;
+  if (ntask == 0) { __syncthreads(); __syncthreads(); return; }
+  int KS = 1;
+  while (KS < 16 && ntask * KS * 2 <= THREADS) KS *= 2;
+  const int kl = ((K + KS - 1) / KS + 7) & ~7;          // slices start on 32-byte boundaries (float4 weight loads)
+  for (int idx = tid; idx < ntask * KS; idx += THREADS) {
+    const int ks = idx / ntask, task = idx - ks * ntask;
+    const int r = task / B, b = task - r * B;
+    const int k0 = ks * kl, k1 = min(K, k0 + kl);
+    const float* w = W + r * K;
+    // 8 independent loads per step and 4 accumulators: the loop is shared-memory-latency bound otherwise
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float* xp = xT + b;
+    int k = k0;
+    for (; k + 7 < k1; k += 8) {
+      const float4 wa = *reinterpret_cast<const float4*>(w + k), wb = *reinterpret_cast<const float4*>(w + k + 4);
+      const float x0 = xp[k * B], x1 = xp[(k + 1) * B], x2 = xp[(k + 2) * B], x3 = xp[(k + 3) * B];
+      const float x4 = xp[(k + 4) * B], x5 = xp[(k + 5) * B], x6 = xp[(k + 6) * B], x7 = xp[(k + 7) * B];
+      a0 = fmaf(wa.x, x0, a0); a1 = fmaf(wa.y, x1, a1); a2 = fmaf(wa.z, x2, a2); a3 = fmaf(wa.w, x3, a3);
+      a0 = fmaf(wb.x, x4, a0); a1 = fmaf(wb.y, x5, a1); a2 = fmaf(wb.z, x6, a2); a3 = fmaf(wb.w, x7, a3);
+    }
+    for (; k < k1; ++k) a0 = fmaf(w[k], xp[k * B], a0);
+    (KS == 1 ? out : part)[idx] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+  if (KS > 1) {
+    for (int task = tid; task < ntask; task += THREADS) {
+      float a = 0.f;
+      for (int ks = 0; ks < KS; ++ks) a += part[ks * ntask + task];
+      out[task] = a;
+    }
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(THREADS, 1) wavernn_kernel(const WrnnParams p) {
@@ -76,23 +117,26 @@ __global__ void __launch_bounds__(THREADS, 1) wavernn_kernel(const WrnnParams p)
   const int s0 = small_head ? 0 : blockIdx.x * ((S + gridDim.x - 1) / gridDim.x);
   const int ns = small_head ? S : max(0, min((S + (int)gridDim.x - 1) / (int)gridDim.x, S - s0));
 
-  // ---- shared-memory carve-up ----
+  // ---- shared-memory carve-up (every array starts on a 16-byte boundary; mirrored by wrnn_geom() on the host) ----
+  const int so_rows = small_head ? S : (S + gridDim.x - 1) / gridDim.x;
   float* W1 = sm;                          // [3][U][H]
   float* wl = W1 + 3 * U * H;              // [3][U]  w_last
-  float* b1 = wl + 3 * U;                  // [3][U]  b_hh1
-  float* W2i = b1 + 3 * U;                 // [3][U][H]   (L == 2)
+  float* b1 = wl + al4(3 * U);             // [3][U]  b_hh1
+  float* W2i = b1 + al4(3 * U);            // [3][U][H]   (L == 2)
   float* W2h = W2i + (p.L == 2 ? 3 * U * H : 0);
   float* b2i = W2h + (p.L == 2 ? 3 * U * H : 0);
-  float* b2h = b2i + (p.L == 2 ? 3 * U : 0);
-  float* Wp = b2h + (p.L == 2 ? 3 * U : 0);   // [P][H]
+  float* b2h = b2i + (p.L == 2 ? al4(3 * U) : 0);
+  float* Wp = b2h + (p.L == 2 ? al4(3 * U) : 0);   // [P][H]
   float* bp = Wp + P * H;                  // [P]
-  float* Wo = bp + P;                      // [ns][256]
-  float* bo = Wo + (small_head ? S : (S + gridDim.x - 1) / gridDim.x) * PRE;   // [ns]
-  float* xin = bo + (small_head ? S : (S + gridDim.x - 1) / gridDim.x);        // [B][H]   layer input / state staging
-  float* hin = xin + B * H;                // [B][H]   (layer 2: previous h2)
-  float* prev = hin + (p.L == 2 ? B * H : 0);   // [B][256]
-  float* lg = prev + B * PRE;              // [B][S] logits (small head) or staging
-  float* lastx = lg + B * max(S, 1);       // [B]
+  float* Wo = bp + al4(P);                 // [so_rows][256]
+  float* bo = Wo + so_rows * PRE;          // [so_rows]
+  float* xin = bo + al4(so_rows);          // [H][B]  layer input (transposed)
+  float* hin = xin + al4(B * H);           // [H][B]  (layer 2: previous h2, transposed)
+  float* prev = hin + (p.L == 2 ? al4(B * H) : 0);   // [256][B]
+  float* lg = prev + al4(B * PRE);         // [S][B] logits
+  float* lastx = lg + al4(B * max(S, 1));  // [B]
+  float* dg = lastx + al4(B);              // [DG][B] dot products (GRU gates: rows [0,3U) input, [3U,6U) hidden)
+  float* part = dg + al4(p.DG * B);        // [THREADS] K-split partial sums
 
   // ---- weights -> smem (once) ----
   for (int g = 0; g < 3; ++g)
@@ -125,75 +169,82 @@ __global__ void __launch_bounds__(THREADS, 1) wavernn_kernel(const WrnnParams p)
   for (int t = 0; t < p.T; ++t) {
     const int nxt = cur ^ 1;
     // ================= layer 1 =================
-    copy_g2s(xin, p.hbuf + cur * hstride, B * H, tid);           // h1(t-1)
+    copy_g2s_T(xin, p.hbuf + cur * hstride, B, H, tid);           // h1(t-1)
     __syncthreads();
-    for (int task = warp; task < nu * B; task += THREADS / 32) {
+    if (nu == U) {
+      dots(W1, 3 * U, xin, B, H, dg, part, tid);            // rows [g*U + u]
+    } else {         // ragged last CTA: its rows are not contiguous across gates - gate by gate
+      for (int g = 0; g < 3; ++g) dots(W1 + g * U * H, nu, xin, B, H, dg + g * U * B, part, tid);
+    }
+    for (int task = tid; task < nu * B; task += THREADS) {
       const int u = task / B, b = task - u * B;
-      const float* hb = xin + b * H;
-      const float dr = dot_ws(W1 + (0 * U + u) * H, hb, H, lane);
-      const float dz = dot_ws(W1 + (1 * U + u) * H, hb, H, lane);
-      const float dn = dot_ws(W1 + (2 * U + u) * H, hb, H, lane);
-      if (lane == 0) {
-        const float lx = lastx[b];
-        const float* gx = p.gx + ((size_t)b * 3 * H + u0 + u) * p.T + t;
-        const float gr = gx[0] + wl[0 * U + u] * lx, gz = gx[(size_t)H * p.T] + wl[1 * U + u] * lx,
-                    gn = gx[(size_t)2 * H * p.T] + wl[2 * U + u] * lx;
-        const float r = sigm(gr + dr + b1[0 * U + u]);
-        const float z = sigm(gz + dz + b1[1 * U + u]);
-        const float n = tanhf(gn + r * (dn + b1[2 * U + u]));
-        p.hbuf[nxt * hstride + (size_t)b * H + u0 + u] = (1.f - z) * n + z * hb[u0 + u];
-      }
+      const float lx = lastx[b];
+      const float* gx = p.gx + ((size_t)b * 3 * H + u0 + u) * p.T + t;
+      const float gr = gx[0] + wl[0 * U + u] * lx, gz = gx[(size_t)H * p.T] + wl[1 * U + u] * lx,
+                  gn = gx[(size_t)2 * H * p.T] + wl[2 * U + u] * lx;
+      const float r = sigm(gr + dg[(0 * U + u) * B + b] + b1[0 * U + u]);
+      const float z = sigm(gz + dg[(1 * U + u) * B + b] + b1[1 * U + u]);
+      const float n = tanhf(gn + r * (dg[(2 * U + u) * B + b] + b1[2 * U + u]));
+      p.hbuf[nxt * hstride + (size_t)b * H + u0 + u] = (1.f - z) * n + z * xin[(u0 + u) * B + b];
     }
     grid.sync();
     // ================= layer 2 =================
     if (p.L == 2) {
-      copy_g2s(xin, p.hbuf + nxt * hstride, B * H, tid);                       // h1(t)
-      copy_g2s(hin, p.hbuf + cur * hstride + (size_t)B * H, B * H, tid);       // h2(t-1)
+      copy_g2s_T(xin, p.hbuf + nxt * hstride, B, H, tid);                       // h1(t)
+      copy_g2s_T(hin, p.hbuf + cur * hstride + (size_t)B * H, B, H, tid);       // h2(t-1)
       __syncthreads();
-      for (int task = warp; task < nu * B; task += THREADS / 32) {
-        const int u = task / B, b = task - u * B;
-        const float *xb = xin + b * H, *hb = hin + b * H;
-        const float ir = dot_ws(W2i + (0 * U + u) * H, xb, H, lane), hr = dot_ws(W2h + (0 * U + u) * H, hb, H, lane);
-        const float iz = dot_ws(W2i + (1 * U + u) * H, xb, H, lane), hz = dot_ws(W2h + (1 * U + u) * H, hb, H, lane);
-        const float in_ = dot_ws(W2i + (2 * U + u) * H, xb, H, lane), hn = dot_ws(W2h + (2 * U + u) * H, hb, H, lane);
-        if (lane == 0) {
-          const float r = sigm(ir + b2i[0 * U + u] + hr + b2h[0 * U + u]);
-          const float z = sigm(iz + b2i[1 * U + u] + hz + b2h[1 * U + u]);
-          const float n = tanhf(in_ + b2i[2 * U + u] + r * (hn + b2h[2 * U + u]));
-          p.hbuf[nxt * hstride + (size_t)B * H + (size_t)b * H + u0 + u] = (1.f - z) * n + z * hb[u0 + u];
+      if (nu == U) {
+        dots(W2i, 3 * U, xin, B, H, dg, part, tid);
+        dots(W2h, 3 * U, hin, B, H, dg + 3 * U * B, part, tid);
+      } else {
+        for (int g = 0; g < 3; ++g) {
+          dots(W2i + g * U * H, nu, xin, B, H, dg + g * U * B, part, tid);
+          dots(W2h + g * U * H, nu, hin, B, H, dg + (3 + g) * U * B, part, tid);
         }
+      }
+      for (int task = tid; task < nu * B; task += THREADS) {
+        const int u = task / B, b = task - u * B;
+        const float* di = dg;
+        const float* dh = dg + 3 * U * B;
+        const float r = sigm(di[(0 * U + u) * B + b] + b2i[0 * U + u] + dh[(0 * U + u) * B + b] + b2h[0 * U + u]);
+        const float z = sigm(di[(1 * U + u) * B + b] + b2i[1 * U + u] + dh[(1 * U + u) * B + b] + b2h[1 * U + u]);
+        const float n = tanhf(di[(2 * U + u) * B + b] + b2i[2 * U + u] + r * (dh[(2 * U + u) * B + b] + b2h[2 * U + u]));
+        p.hbuf[nxt * hstride + (size_t)B * H + (size_t)b * H + u0 + u] = (1.f - z) * n + z * hin[(u0 + u) * B + b];
       }
       grid.sync();
     }
     // ================= pre-output: tanh(W h + b) =================
-    copy_g2s(xin, p.hbuf + nxt * hstride + (size_t)(p.L - 1) * B * H, B * H, tid);   // top layer's h(t)
+    copy_g2s_T(xin, p.hbuf + nxt * hstride + (size_t)(p.L - 1) * B * H, B, H, tid);   // top layer's h(t)
     __syncthreads();
-    for (int task = warp; task < np * B; task += THREADS / 32) {
+    dots(Wp, np, xin, B, H, dg, part, tid);
+    for (int task = tid; task < np * B; task += THREADS) {
       const int r = task / B, b = task - r * B;
-      const float d = dot_ws(Wp + r * H, xin + b * H, H, lane);
-      if (lane == 0) p.prebuf[(size_t)b * PRE + p0 + r] = tanhf(d + bp[r]);
+      p.prebuf[(size_t)b * PRE + p0 + r] = tanhf(dg[task] + bp[r]);
     }
     grid.sync();
     // ================= output layer + sampling head =================
-    copy_g2s(prev, p.prebuf, B * PRE, tid);
+    copy_g2s_T(prev, p.prebuf, B, PRE, tid);
     __syncthreads();
-    for (int task = warp; task < ns * B; task += THREADS / 32) {
-      const int r = task / B, b = task - r * B;
-      const float d = dot_ws(Wo + r * PRE, prev + b * PRE, PRE, lane) + bo[r];
-      if (lane == 0) {
-        if (small_head) lg[b * S + r] = d;
-        else p.logits[(size_t)b * S + s0 + r] = d;
+    if (small_head) {
+      dots(Wo, ns, prev, B, PRE, lg, part, tid);          // lg[s*B + b]
+    } else {
+      dots(Wo, ns, prev, B, PRE, dg, part, tid);          // ns <= ceil(256/G) rows: fits dg
+      for (int task = tid; task < ns * B; task += THREADS) {
+        const int r = task / B, b = task - r * B;
+        p.logits[(size_t)b * S + s0 + r] = dg[task] + bo[r];
       }
-    }
-    if (!small_head) {
       grid.sync();
-      copy_g2s(lg, p.logits, B * S, tid);
+      for (int i = tid; i < B * S; i += THREADS) {         // [B][S] -> lg[s*B + b]
+        const int b = i / S, k = i - b * S;
+        lg[k * B + b] = p.logits[i];
+      }
+      __syncthreads();
     }
-    __syncthreads();
     if (p.head == HEAD_MOL || p.head == HEAD_GM) {
       if (tid < B) {
         const int b = tid;
-        const float* y = lg + b * S;
+        float y[32];
+        for (int k = 0; k < S; ++k) y[k] = lg[k * B + b] + bo[k];     // small head: bias added here
         float x;
         if (p.head == HEAD_MOL) {       // cube/networks/loss.py:176-199
           const int nm = S / 3;
@@ -215,12 +266,11 @@ __global__ void __launch_bounds__(THREADS, 1) wavernn_kernel(const WrnnParams p)
       }
     } else {                            // categorical heads: Gumbel-max over S logits, one warp per batch item
       for (int b = warp; b < B; b += THREADS / 32) {
-        const float* y = lg + b * S;
         const float* u = p.draws + ((size_t)t * B + b) * S;
         float bs = -__builtin_inff();
         int bi = 0x7fffffff;
         for (int k = lane; k < S; k += 32) {
-          const float s = y[k] - logf(-logf(u[k]));
+          const float s = lg[k * B + b] - logf(-logf(u[k]));
           if (s > bs) { bs = s; bi = k; }
         }
 #pragma unroll
