@@ -68,7 +68,7 @@ struct TcPacked {
   int N = 0, n_tiles = 0, nchunks_total = 0, nseg = 0;
   int bn = 256, nphase = 1;
   long long w_phase_stride = 0;
-  tc::TcSeg seg[2];
+  tc::TcSeg seg[2];   // logical segments (a window-mode launch may split them, see launch_tc_t)
 };
 
 }  // namespace cube
@@ -832,6 +832,12 @@ static int forward_hifigan(cube_voc* h, const float* mel, const int32_t* n_frame
 // forward: HiFi-GAN on tensor cores.  Every MMA-input tensor is stored leaky-ReLU'd (slope 0.1) as
 // fp16 hi/lo planes, channels-last; the residual stream is recovered from it by the inverse map.
 // ------------------------------------------------------------------------------------------------
+static bool use_win() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CUBE_TC_WIN"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 static bool use_cg2() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("CUBE_TC_CG2"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -864,15 +870,50 @@ static void launch_tc_t(cube_voc* h, tc::TcParams& tp, cudaStream_t st) {
     cudaLaunchKernelEx(&cfg, tc::tc_conv_kernel<TN, true>, tp);
     return;
   }
+  constexpr int rows1 = tc::BM * tc::Cfg<TN, false>::MSUB;
+  tp.t_tiles = (tp.T + rows1 - 1) / rows1;
+  const long long tiles = (long long)tp.n_tiles * tp.t_tiles * tp.B * nph;
+  const int grid = (int)std::min<long long>(tiles, h->sm_count);
+  if (use_win()) {
+    // window mode: one staged A window per channel chunk serves all taps whose span fits one extra box;
+    // wider dilations (ClariNet d = 81, 243) become single-tap segments
+    tc::TcParams wp = tp;
+    wp.nseg = 0;
+    int base = 0;
+    bool ok = true;
+    for (int s_ = 0; s_ < tp.nseg && ok; ++s_) {
+      const tc::TcSeg sg = tp.seg[s_];
+      const int span = (sg.taps - 1) * sg.dil;
+      if (span <= tc::BM) {
+        if (wp.nseg >= tc::MAX_SEG) { ok = false; break; }
+        tc::TcSeg n = sg;
+        n.src = s_; n.wchunk0 = base; n.nbox = (rows1 + span + tc::BM - 1) / tc::BM;
+        wp.seg[wp.nseg++] = n;
+      } else {
+        for (int j = 0; j < sg.taps; ++j) {
+          if (wp.nseg >= tc::MAX_SEG) { ok = false; break; }
+          tc::TcSeg n = sg;
+          n.taps = 1; n.off0 = sg.off0 + j * sg.dil; n.src = s_; n.wchunk0 = base + j * sg.nchunks; n.nbox = rows1 / tc::BM;
+          wp.seg[wp.nseg++] = n;
+        }
+      }
+      base += sg.taps * sg.nchunks;
+    }
+    if (ok) {
+      static bool attrw[64] = {false};
+      if (!attrw[h->device & 63]) {
+        cudaFuncSetAttribute(tc::tc_conv_kernel<TN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WinCfg<TN>::SMEM);
+        attrw[h->device & 63] = true;
+      }
+      tc::tc_conv_kernel<TN, false, true><<<grid, tc::NUM_THREADS, tc::WinCfg<TN>::SMEM, st>>>(wp);
+      return;
+    }
+  }
   static bool attr[64] = {false};
   if (!attr[h->device & 63]) {
     cudaFuncSetAttribute(tc::tc_conv_kernel<TN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<TN, false>::SMEM);
     attr[h->device & 63] = true;
   }
-  constexpr int rows1 = tc::BM * tc::Cfg<TN, false>::MSUB;
-  tp.t_tiles = (tp.T + rows1 - 1) / rows1;
-  const long long tiles = (long long)tp.n_tiles * tp.t_tiles * tp.B * nph;
-  const int grid = (int)std::min<long long>(tiles, h->sm_count);
   tc::tc_conv_kernel<TN, false><<<grid, tc::NUM_THREADS, tc::Cfg<TN, false>::SMEM, st>>>(tp);
 }
 
