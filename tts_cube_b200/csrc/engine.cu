@@ -832,10 +832,14 @@ static int forward_hifigan(cube_voc* h, const float* mel, const int32_t* n_frame
 // forward: HiFi-GAN on tensor cores.  Every MMA-input tensor is stored leaky-ReLU'd (slope 0.1) as
 // fp16 hi/lo planes, channels-last; the residual stream is recovered from it by the inverse map.
 // ------------------------------------------------------------------------------------------------
-static bool use_win() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("CUBE_TC_WIN"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
+// window mode (tc_conv.cuh): measured +4 % on the HiFi-GAN generator (its k=7/11 taps re-read the same rows), -12 % on
+// the student (3 taps only, and the window ring leaves a shallower weight ring) -> default on for HiFi-GAN only;
+// CUBE_TC_WIN=0/1 overrides for experiments
+static bool use_win(const cube_voc* h) {
+  static int v = -2;
+  if (v == -2) { const char* e = getenv("CUBE_TC_WIN"); v = e ? (e[0] == '1' ? 1 : 0) : -1; }
+  if (v >= 0) return v == 1;
+  return h->cfg.arch == CUBE_VOC_HIFIGAN;
 }
 
 static bool use_cg2() {
@@ -874,7 +878,7 @@ static void launch_tc_t(cube_voc* h, tc::TcParams& tp, cudaStream_t st) {
   tp.t_tiles = (tp.T + rows1 - 1) / rows1;
   const long long tiles = (long long)tp.n_tiles * tp.t_tiles * tp.B * nph;
   const int grid = (int)std::min<long long>(tiles, h->sm_count);
-  if (use_win()) {
+  if (use_win(h)) {
     // window mode: one staged A window per channel chunk serves all taps whose span fits one extra box;
     // wider dilations (ClariNet d = 81, 243) become single-tap segments
     tc::TcParams wp = tp;
