@@ -581,6 +581,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
     const int row = q * 32 + lane;          // tile row = time step within the tile
     const int etid = threadIdx.x - 64;      // 0..511
     uint32_t titer = 0;
+    int sb_nt = -1;                         // column tile whose (de-scale, bias) pairs are in s_sb
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++titer) {
       const int nt = tile % p.n_tiles;
       int rest = tile / p.n_tiles;
@@ -590,16 +591,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
       const uint32_t acc = titer & 1, aph = (titer >> 1) & 1;
       // per-column (de-scale, bias) of this tile -> smem.  For the gate the exp2 pre-factors are
       // folded in: filter columns carry 2*log2(e) (-> 2^a = e^{2f}), gate columns -log2(e) (-> e^{-g}).
-      asm volatile("bar.sync 1, 512;" ::: "memory");   // previous tile's readers are done
-      if (etid < BN) {
-        float sc = __ldg(p.inv_scale + nt * BN + etid) * p.a_inv_scale, bi = __ldg(p.bias + nt * BN + etid);
-        if (p.epi == TC_EPI_GATE) {
-          const float k = etid < BN / 2 ? 2.f * LOG2E : -LOG2E;
-          sc *= k; bi *= k;
+      if (nt != sb_nt) {   // (re)load only when the column tile changes: with an even grid it never does after the first tile
+        asm volatile("bar.sync 1, 512;" ::: "memory");   // previous tile's readers are done
+        if (etid < BN) {
+          float sc = __ldg(p.inv_scale + nt * BN + etid) * p.a_inv_scale, bi = __ldg(p.bias + nt * BN + etid);
+          if (p.epi == TC_EPI_GATE) {
+            const float k = etid < BN / 2 ? 2.f * LOG2E : -LOG2E;
+            sc *= k; bi *= k;
+          }
+          s_sb[etid] = make_float2(sc, bi);
         }
-        s_sb[etid] = make_float2(sc, bi);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        sb_nt = nt;
       }
-      asm volatile("bar.sync 1, 512;" ::: "memory");
       const uint32_t taddr = tmem_base + (acc * MSUB + msub) * BN + ((uint32_t)(q * 32) << 16);
       const int len = p.lens ? min(p.lens[b], p.T) : p.T;
       const bool in_range = t < p.T;
