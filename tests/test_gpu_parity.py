@@ -396,3 +396,21 @@ def test_cubenet_vocoder_fold(dev):
     # hr chunk: 3 frames x 20 = 60 vs (10 + 4) low samples x 4 = 56 -> T = 56 (the reference's min()), minus the 20-sample context
     assert x_lr.shape == (1, 40 * 5, 1) and x_hr.shape == (1, 20 * (56 - 20))
     assert np.isfinite(x_lr).all() and bool(torch.isfinite(x_hr).all())
+
+
+def test_hifigan_tcgen05_edge_cases(dev):
+    """Tensor-core path: a single frame (every TMA box mostly out of bounds), an empty utterance in a batch, batch of
+    one, odd lengths - against the oracle."""
+    cfg = dict(H.CONFIG_V1)
+    sd = H.random_state_dict(cfg, seed=21, std=0.3, g_scale=0.125)
+    g = _gen(cfg, sd, dev, 1)
+    with torch.no_grad():
+        for F_, frames in ((1, None), (2, None), (7, [0, 7, 3])):
+            B = len(frames) if frames else 1
+            mel = H.synthetic_mel(B, F_, seed=40 + F_)
+            y = g(mel.to(dev), n_frames=frames).cpu()
+            ref = H.generator_forward_ragged(sd, cfg, mel, frames) if frames else H.generator_forward(sd, cfg, mel)
+            assert y.shape == ref.shape
+            assert float((y - ref).abs().max()) <= TOL, (F_, frames)
+            if frames:
+                assert float(y[0].abs().max()) == 0.0
