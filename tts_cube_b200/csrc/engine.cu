@@ -17,9 +17,13 @@
 #include "conv_simt.cuh"
 #include "heads.cuh"
 #include "tc_conv.cuh"
+#include "tc_block.cuh"
 #include "wavernn.cuh"
 
 #define CUBE_VERSION "0.1.0"
+#ifndef CUBE_FUSED_DEFAULT
+#define CUBE_FUSED_DEFAULT false
+#endif
 
 namespace cube {
 
@@ -842,6 +846,13 @@ static bool use_win(const cube_voc* h) {
   return h->cfg.arch == CUBE_VOC_HIFIGAN;
 }
 
+// fused residual-block kernel (tc_block.cuh) for the student: CUBE_TC_FUSED=0/1 overrides the default
+static bool use_fused() {
+  static int v = -2;
+  if (v == -2) { const char* e = getenv("CUBE_TC_FUSED"); v = e ? (e[0] == '1' ? 1 : 0) : -1; }
+  return v < 0 ? CUBE_FUSED_DEFAULT : v == 1;
+}
+
 static bool use_cg2() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("CUBE_TC_CG2"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -1159,6 +1170,31 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
     const int nb = c.flow_blocks[f];
     for (int i = 0; i < nb; ++i) {
       const int d = dilation_of(c, i);
+      if (use_tc && use_fused() && K * (R / tc::BK) + (CI + tc::BK - 1) / tc::BK == fl.tc_gate[i].nchunks_total && G == 256) {
+        // whole residual block in one kernel: o stays on chip (tc_block.cuh)
+        lx.begin("block_fused");
+        tc::BlockParams bp;
+        memset(&bp, 0, sizeof(bp));
+        bp.tmH = tm_h; bp.tmC = tm_c;
+        bp.W1 = fl.tc_gate[i].Wimg; bp.inv1 = fl.tc_gate[i].inv_scale; bp.bias1 = fl.tc_gate[i].bias;
+        bp.W2 = fl.tc_resskip[i].Wimg; bp.inv2 = fl.tc_resskip[i].inv_scale; bp.bias2 = fl.tc_resskip[i].bias;
+        bp.taps = K; bp.dil = d; bp.off0 = -(K - 1) * d;
+        bp.h_chunks = R / tc::BK; bp.c_chunks = (CI + tc::BK - 1) / tc::BK;
+        bp.c_last_ksteps = ((CI - (bp.c_chunks - 1) * tc::BK) + 15) / 16;
+        bp.B = B; bp.T = T; bp.t_tiles = (T + tc::BM - 1) / tc::BM;
+        bp.lens = lens_T; bp.h16 = h16; bp.skip = sk; bp.skip_set = (i == 0); bp.scale = rs;
+        bp.skip16 = (i == nb - 1) ? s16 : nullptr;
+        static bool attrb[64] = {false};
+        if (!attrb[h->device & 63]) {
+          CU_TRY(cudaFuncSetAttribute(tc::tc_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::BLK_SMEM));
+          attrb[h->device & 63] = true;
+        }
+        const long long tiles = (long long)bp.t_tiles * B;
+        tc::tc_block_kernel<<<(int)std::min<long long>(tiles, h->sm_count), tc::NUM_THREADS, tc::BLK_SMEM, st>>>(bp);
+        lx.check();
+        lx.end();
+        continue;
+      }
       if (use_tc) {
         {  // o = tanh(filter(h) + filter_c(c)) * sigmoid(gate(h) + gate_c(c))   [tcgen05]
           lx.begin("gate");

@@ -1,0 +1,369 @@
+// One ClariNet residual block in ONE tcgen05 kernel (sm_100a):
+//     f|g = W1 . [h(t-2d), h(t-d), h(t), c(t)]      GEMM1  [128 rows x 512]   K = 3*128 + 80
+//     o   = tanh(f) * sigmoid(g)                     stays ON CHIP (TMEM -> registers -> swizzled smem A tiles)
+//     r|s = W2 . o                                   GEMM2  [128 rows x 256]   K = 256
+//     h   = (h + r) * sqrt(.5)  (in place, fp16 planes),   skip (+)= s  (fp32)
+// The unfused pair (tc_conv_kernel GATE + RESSKIP) writes o (1.8 GB per block at B=8 x 10 s) to HBM and reads it
+// back, and its tensor-bound half (gate) and HBM-bound half (res/skip) run back to back; here o never leaves the
+// SM and the residual/skip traffic of tile i hides under the MMAs of tile i+1.
+//
+// TMEM: two 256-column regions X, Y.  Per tile (parity p swaps the roles): GEMM1 n-tile 0 -> R0, GEMM1 n-tile 1 ->
+// R1, GEMM2 (both K halves) -> R0 again once its gate epilogue has drained it.  The next tile starts in this tile's
+// R1, which is free long before this tile's res/skip epilogue runs.
+// smem: 3-stage ring of 48 KB (A hi/lo 8 KB each by TMA + one 256-row weight chunk hi/lo 16 KB each by bulk copy;
+// GEMM2 stages carry weights only), a 64 KB buffer for one K-half of o as four K-major SWIZZLE_64B A tiles per plane,
+// 6 KB of folded (de-scale, bias) pairs.  Roles as in tc_conv_kernel: warp 0 TMA, warp 1 MMA, warps 2-17 epilogue.
+#pragma once
+#include "tc_conv.cuh"
+
+namespace cube {
+namespace tc {
+
+constexpr int BLK_STAGES = 3;
+constexpr int BLK_STAGE_BYTES = 2 * A_TILE_BYTES + 2 * (256 * BK * 2);    // 48 KB
+constexpr int BLK_O_BYTES = 2 * 4 * A_TILE_BYTES;                         // 4 chunks x (hi, lo) = 64 KB
+constexpr int BLK_SMEM = BLK_STAGES * BLK_STAGE_BYTES + BLK_O_BYTES + 1024 + 256 + 768 * 8;
+static_assert(BK == 32, "tc_block_kernel is written for 32-channel K chunks (SWIZZLE_64B)");
+
+struct BlockParams {
+  CUtensorMap tmH, tmC;          // h16 [2B][T][128], c16 [2B][T][80]
+  const __half* W1;              // gate images   [2 n-tiles][nch1][2][256*32]
+  const __half* W2;              // res/skip images [1][8][2][256*32]
+  const float* inv1; const float* bias1;   // [512]  (n-tile major: [nt*256 + col])
+  const float* inv2; const float* bias2;   // [256]
+  int taps, dil, off0;           // h segment: taps at rows t + off0 + j*dil
+  int h_chunks, c_chunks, c_last_ksteps;   // K chunks per tap of h (4), of c (3), K steps in c's last chunk (1)
+  int B, T, t_tiles;
+  const int* lens;
+  __half* h16; float* skip; int skip_set; __half* skip16; float scale;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_constant__ BlockParams p) {
+  constexpr int BN = 256;
+  constexpr int B_BYTES = BN * BK * 2;             // 16 KB per plane
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* o_smem = smem + BLK_STAGES * BLK_STAGE_BYTES;      // [4 chunks][hi 8 KB | lo 8 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(o_smem + BLK_O_BYTES);
+  uint64_t* full = bars;                       // [3]
+  uint64_t* empty = bars + BLK_STAGES;         // [3]
+  uint64_t* acc_full = bars + 2 * BLK_STAGES;  // [2] region holds a finished accumulator        (MMA -> epilogue)
+  uint64_t* acc_free = acc_full + 2;           // [2] region drained                             (epilogue -> MMA, 16 warps)
+  uint64_t* o_full = acc_free + 2;             // [1] o half is in smem                          (epilogue -> MMA, 16 warps)
+  uint64_t* o_free = o_full + 1;               // [1] GEMM2 has read the o half                  (MMA -> epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+  float2* sb1 = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [512] gate: folded exp2 factors
+  float2* sb2 = sb1 + 512;                                                           // [256] res/skip
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.t_tiles * p.B;
+  const int nch1 = p.taps * p.h_chunks + p.c_chunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmH);
+    prefetch_tmap(&p.tmC);
+    for (int s = 0; s < BLK_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int r = 0; r < 2; ++r) { mbar_init(&acc_full[r], 1); mbar_init(&acc_free[r], NUM_EPI_WARPS); }
+    mbar_init(o_full, NUM_EPI_WARPS);
+    mbar_init(o_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  {  // folded per-column constants, once per CTA (this CTA owns all 512 + 256 columns)
+    constexpr float LOG2E = 1.4426950408889634f;
+    for (int i = threadIdx.x; i < 512; i += NUM_THREADS) {
+      const float k = (i & 255) < 128 ? 2.f * LOG2E : -LOG2E;     // filter cols -> e^{2f}, gate cols -> e^{-g}
+      sb1[i] = make_float2(__ldg(p.inv1 + i) * k, __ldg(p.bias1 + i) * k);
+    }
+    for (int i = threadIdx.x; i < 256; i += NUM_THREADS) sb2[i] = make_float2(__ldg(p.inv2 + i), __ldg(p.bias2 + i));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tt = tile % p.t_tiles, b = tile / p.t_tiles;
+        const int t0 = tt * BM;
+        for (int nt = 0; nt < 2; ++nt) {                       // GEMM1, one 256-column n-tile at a time
+          const __half* wt = p.W1 + (size_t)nt * nch1 * 2 * (BN * BK);
+          int chunk = 0;
+          for (int tap = 0; tap <= p.taps; ++tap) {            // tap == p.taps: the conditioning segment
+            const bool cond = tap == p.taps;
+            const int row = cond ? t0 : t0 + p.off0 + tap * p.dil;
+            const int ncc = cond ? p.c_chunks : p.h_chunks;
+            for (int cc = 0; cc < ncc; ++cc, ++chunk, ++it) {
+              const int st = it % BLK_STAGES;
+              mbar_wait(&empty[st], ((it / BLK_STAGES) & 1) ^ 1);
+              uint8_t* sb = smem + st * BLK_STAGE_BYTES;
+              mbar_expect_tx(&full[st], BLK_STAGE_BYTES);
+              const CUtensorMap* tm = cond ? &p.tmC : &p.tmH;
+              tma_load_3d(sb, tm, &full[st], cc * BK, row, b);
+              tma_load_3d(sb + A_TILE_BYTES, tm, &full[st], cc * BK, row, p.B + b);
+              const __half* wc = wt + (size_t)chunk * 2 * (BN * BK);
+              bulk_load(sb + 2 * A_TILE_BYTES, wc, B_BYTES, &full[st]);
+              bulk_load(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, &full[st]);
+            }
+          }
+        }
+        for (int ch = 0; ch < 8; ++ch, ++it) {                 // GEMM2: weights only (its A operand is o, on chip)
+          const int st = it % BLK_STAGES;
+          mbar_wait(&empty[st], ((it / BLK_STAGES) & 1) ^ 1);
+          uint8_t* sb = smem + st * BLK_STAGE_BYTES;
+          mbar_expect_tx(&full[st], 2 * B_BYTES);
+          const __half* wc = p.W2 + (size_t)ch * 2 * (BN * BK);
+          bulk_load(sb + 2 * A_TILE_BYTES, wc, B_BYTES, &full[st]);
+          bulk_load(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, &full[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, BM);
+      uint32_t it = 0, titer = 0;
+      uint32_t free_ph[2] = {0, 0};        // completed-phase counters of acc_free[r] this thread has consumed
+      uint32_t ofull_ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
+        const int r0 = titer & 1, r1 = r0 ^ 1;      // region roles of this tile
+        for (int nt = 0; nt < 2; ++nt) {
+          const int rg = nt == 0 ? r0 : r1;
+          // the region must have been drained by its previous user (first use of each region: passes at once)
+          mbar_wait(&acc_free[rg], (free_ph[rg] & 1) ^ 1);
+          ++free_ph[rg];
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + rg * BN;
+          uint32_t accumulate = 0;
+          for (int tap = 0; tap <= p.taps; ++tap) {
+            const bool cond = tap == p.taps;
+            const int ncc = cond ? p.c_chunks : p.h_chunks;
+            for (int cc = 0; cc < ncc; ++cc, ++it) {
+              const int st = it % BLK_STAGES;
+              mbar_wait(&full[st], (it / BLK_STAGES) & 1);
+              tc_fence_after();
+              const uint32_t a_hi = smem_u32(smem + st * BLK_STAGE_BYTES), a_lo = a_hi + A_TILE_BYTES;
+              const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + B_BYTES;
+              const int ksteps = (cond && cc == ncc - 1) ? p.c_last_ksteps : (BK / 16);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t ko = ks * 32;
+                umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
+                umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+                umma_f16(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                accumulate = 1;
+              }
+              umma_commit(&empty[st]);
+            }
+          }
+          umma_commit(&acc_full[rg]);
+        }
+        // GEMM2 into r0 (drained by the gate epilogue of n-tile 0): K half kh uses the o half the epilogue staged
+        {
+          mbar_wait(&acc_free[r0], (free_ph[r0] & 1) ^ 1);
+          ++free_ph[r0];
+          const uint32_t d_tmem = tmem_base + r0 * BN;
+          uint32_t accumulate = 0;
+          for (int kh = 0; kh < 2; ++kh) {
+            mbar_wait(o_full, ofull_ph & 1);
+            ++ofull_ph;
+            tc_fence_after();
+            for (int c4 = 0; c4 < 4; ++c4, ++it) {
+              const int st = it % BLK_STAGES;
+              mbar_wait(&full[st], (it / BLK_STAGES) & 1);
+              tc_fence_after();
+              const uint32_t a_hi = smem_u32(o_smem + c4 * 2 * A_TILE_BYTES), a_lo = a_hi + A_TILE_BYTES;
+              const uint32_t b_hi = smem_u32(smem + st * BLK_STAGE_BYTES) + 2 * A_TILE_BYTES, b_lo = b_hi + B_BYTES;
+              for (int ks = 0; ks < BK / 16; ++ks) {
+                const uint32_t ko = ks * 32;
+                umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
+                umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+                umma_f16(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                accumulate = 1;
+              }
+              umma_commit(&empty[st]);
+            }
+            umma_commit(o_free);          // the o half may be overwritten
+          }
+          umma_commit(&acc_full[r0]);     // r|s accumulator complete
+        }
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 2..17) ===========================
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int grp = (warp - 2) >> 2;        // 0..3
+    const int row = q * 32 + lane;
+    uint32_t titer = 0;
+    uint32_t full_ph[2] = {0, 0};           // uses of acc_full[r] consumed so far
+    uint32_t ofree_ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
+      const int tt = tile % p.t_tiles, b = tile / p.t_tiles;
+      const int t = tt * BM + row;
+      const int r0 = titer & 1, r1 = r0 ^ 1;
+      const int len = p.lens ? min(p.lens[b], p.T) : p.T;
+      const bool in_range = t < p.T, valid = t < len;
+      // pull this tile's residual rows / skip columns into L2 while the MMAs run
+      if (in_range) {
+        if (grp < 2) {
+          const __half* h0 = p.h16 + ((size_t)b * p.T + t) * 128 + grp * 64;
+          prefetch_l2(h0);
+          prefetch_l2(h0 + (size_t)p.B * p.T * 128);
+        } else if (!p.skip_set && (lane & 7) == 0) {
+          const float* s0 = p.skip + ((size_t)b * 128 + (grp - 2) * 64) * p.T + t;
+#pragma unroll 8
+          for (int j = 0; j < 64; ++j) prefetch_l2(s0 + (size_t)j * p.T);
+        }
+      }
+      // ---------------- gate epilogue of n-tile 0 (region r0) and n-tile 1 (region r1) ----------------
+      for (int nt = 0; nt < 2; ++nt) {
+        const int rg = nt == 0 ? r0 : r1;
+        mbar_wait(&acc_full[rg], full_ph[rg] & 1);
+        ++full_ph[rg];
+        // the o buffer is free once GEMM2 has consumed the previous half (first half ever: passes at once)
+        mbar_wait(o_free, (ofree_ph & 1) ^ 1);
+        ++ofree_ph;
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + rg * BN + ((uint32_t)(q * 32) << 16);
+        const float2* sb = sb1 + nt * 256;
+        // this warp: output channels [32*grp, +32) of this n-tile = K chunk `grp` of the o half
+        uint8_t* otile = o_smem + grp * 2 * A_TILE_BYTES;
+#pragma unroll
+        for (int cc = 0; cc < 32; cc += 16) {
+          uint32_t f[16], g[16];
+          tmem_ld16(taddr + grp * 32 + cc, f);
+          tmem_ld16(taddr + 128 + grp * 32 + cc, g);
+          tmem_ld_wait();
+          uint32_t hi2[8], lo2[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            float o[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float2 sf = sb[grp * 32 + cc + j + u], sg = sb[128 + grp * 32 + cc + j + u];
+              const float a = fminf(fmaxf(fmaf(__uint_as_float(f[j + u]), sf.x, sf.y), -40.f), 40.f);
+              const float e = fminf(fmaf(__uint_as_float(g[j + u]), sg.x, sg.y), 60.f);
+              const float E1 = ex2_fast(a), E2 = ex2_fast(e);
+              o[u] = valid ? (E1 - 1.f) * rcp_fast((E1 + 1.f) * (1.f + E2)) : 0.f;
+            }
+            split16x2(o[0], o[1], hi2[j >> 1], lo2[j >> 1]);
+          }
+          // K-major SWIZZLE_64B A tile [128 rows][32 ch]: 16-byte piece c16 of row r lives at piece c16 ^ ((r>>1)&3)
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const int c16 = (cc >> 3) + v;
+            const uint32_t off = row * 64 + ((c16 ^ ((row >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(otile + off) = make_uint4(hi2[4 * v], hi2[4 * v + 1], hi2[4 * v + 2], hi2[4 * v + 3]);
+            *reinterpret_cast<uint4*>(otile + A_TILE_BYTES + off) = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
+          }
+        }
+        fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(o_full); mbar_arrive(&acc_free[rg]); }
+      }
+      // ---------------- res/skip epilogue (GEMM2 result in region r0) ----------------
+      mbar_wait(&acc_full[r0], full_ph[r0] & 1);
+      ++full_ph[r0];
+      tc_fence_after();
+      {
+        const uint32_t taddr = tmem_base + r0 * BN + ((uint32_t)(q * 32) << 16);
+        if (grp < 2) {   // cols [0,128): residual stream in place; this warp: channels [64*grp, +64)
+          const size_t plane = (size_t)p.B * p.T * 128;
+          __half* hrow = p.h16 + ((size_t)b * p.T + t) * 128;
+#pragma unroll
+          for (int cc = grp * 64; cc < grp * 64 + 64; cc += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + cc, r);
+            uint4 hv[2], lv[2];
+            if (in_range) {
+#pragma unroll
+              for (int v = 0; v < 2; ++v) {
+                hv[v] = reinterpret_cast<const uint4*>(hrow + cc)[v];
+                lv[v] = reinterpret_cast<const uint4*>(hrow + plane + cc)[v];
+              }
+            } else {
+              hv[0] = hv[1] = lv[0] = lv[1] = make_uint4(0, 0, 0, 0);
+            }
+            tmem_ld_wait();
+            const uint32_t* hp = reinterpret_cast<const uint32_t*>(hv);
+            const uint32_t* lp = reinterpret_cast<const uint32_t*>(lv);
+            uint32_t hi2[8], lo2[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const float2 s0 = sb2[cc + j], s1 = sb2[cc + j + 1];
+              const float2 oh = unpack_h2(hp[j >> 1]), ol = unpack_h2(lp[j >> 1]);
+              const float v0 = fmaf(__uint_as_float(r[j]), s0.x, s0.y), v1 = fmaf(__uint_as_float(r[j + 1]), s1.x, s1.y);
+              const float n0 = valid ? ((oh.x + ol.x) + v0) * p.scale : 0.f;
+              const float n1 = valid ? ((oh.y + ol.y) + v1) * p.scale : 0.f;
+              split16x2(n0, n1, hi2[j >> 1], lo2[j >> 1]);
+            }
+            if (in_range) {
+#pragma unroll
+              for (int v = 0; v < 2; ++v) {
+                reinterpret_cast<uint4*>(hrow + cc)[v] = make_uint4(hi2[4 * v], hi2[4 * v + 1], hi2[4 * v + 2], hi2[4 * v + 3]);
+                reinterpret_cast<uint4*>(hrow + plane + cc)[v] = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
+              }
+            }
+          }
+        } else {         // cols [128,256): skip accumulator; this warp: skip channels [64*(grp-2), +64)
+          float* sp0 = p.skip + (size_t)b * 128 * p.T + t;
+#pragma unroll
+          for (int cc = (grp - 2) * 64; cc < (grp - 2) * 64 + 64; cc += 16) {
+            uint32_t r[16];
+            float old[16];
+            tmem_ld16(taddr + 128 + cc, r);
+            if (in_range && !p.skip_set) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) old[j] = __ldcs(sp0 + (size_t)(cc + j) * p.T);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) old[j] = 0.f;
+            }
+            tmem_ld_wait();
+            if (p.skip16) {
+              uint32_t hi2[8], lo2[8];
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const float2 s0 = sb2[128 + cc + j], s1 = sb2[128 + cc + j + 1];
+                const float y0 = old[j] + fmaf(__uint_as_float(r[j]), s0.x, s0.y);
+                const float y1 = old[j + 1] + fmaf(__uint_as_float(r[j + 1]), s1.x, s1.y);
+                split16x2(valid ? fmaxf(y0, 0.f) : 0.f, valid ? fmaxf(y1, 0.f) : 0.f, hi2[j >> 1], lo2[j >> 1]);
+              }
+              if (in_range) {
+                __half* srow = p.skip16 + ((size_t)b * p.T + t) * 128 + cc;
+                const size_t splane = (size_t)p.B * p.T * 128;
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                  reinterpret_cast<uint4*>(srow)[v] = make_uint4(hi2[4 * v], hi2[4 * v + 1], hi2[4 * v + 2], hi2[4 * v + 3]);
+                  reinterpret_cast<uint4*>(srow + splane)[v] = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
+                }
+              }
+            } else if (in_range) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float2 s2 = sb2[128 + cc + j];
+                const float y = old[j] + fmaf(__uint_as_float(r[j]), s2.x, s2.y);
+                __stcs(sp0 + (size_t)(cc + j) * p.T, valid ? y : 0.f);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_free[r0]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace tc
+}  // namespace cube
