@@ -1121,13 +1121,19 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
   const float* zin = noise;
   const float rs = sqrtf(0.5f);
   const bool use_tc = (c.math == CUBE_MATH_TC_SPLIT16);
-  __half *h16 = nullptr, *o16 = nullptr, *c16 = nullptr, *s16 = nullptr;
-  CUtensorMap tm_h, tm_o, tm_c, tm_s;
+  __half *h16 = nullptr, *h16b = nullptr, *o16 = nullptr, *c16 = nullptr, *s16 = nullptr;
+  CUtensorMap tm_h, tm_hb, tm_o, tm_c, tm_s;
   if (use_tc) {
     float *t1, *t2, *t3, *t4;
     if (ws_get(h, "s16", (size_t)B * T * S, &t4)) return 1;
     s16 = (__half*)t4;
     if (make_tmap_hl16(&tm_s, s16, B, T, S)) return 1;
+    if (use_fused()) {   // the fused block kernel ping-pongs the residual stream between two buffers
+      float* t5;
+      if (ws_get(h, "h16b", (size_t)B * T * R, &t5)) return 1;
+      h16b = (__half*)t5;
+      if (make_tmap_hl16(&tm_hb, h16b, B, T, R)) return 1;
+    }
     // fp16 (hi, lo) planes, channels-last: 2*2 bytes per element = the footprint of one fp32 tensor
     if (ws_get(h, "h16", (size_t)B * T * R, &t1) || ws_get(h, "o16", (size_t)B * T * G, &t2) ||
         ws_get(h, "c16", (size_t)B * T * CI, &t3)) return 1;
@@ -1176,13 +1182,14 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
         tc::BlockParams bp;
         memset(&bp, 0, sizeof(bp));
         bp.tmH = tm_h; bp.tmC = tm_c;
+        bp.h_in16 = h16; bp.h_out16 = h16b;
         bp.W1 = fl.tc_gate[i].Wimg; bp.inv1 = fl.tc_gate[i].inv_scale; bp.bias1 = fl.tc_gate[i].bias;
         bp.W2 = fl.tc_resskip[i].Wimg; bp.inv2 = fl.tc_resskip[i].inv_scale; bp.bias2 = fl.tc_resskip[i].bias;
         bp.taps = K; bp.dil = d; bp.off0 = -(K - 1) * d;
         bp.h_chunks = R / tc::BK; bp.c_chunks = (CI + tc::BK - 1) / tc::BK;
         bp.c_last_ksteps = ((CI - (bp.c_chunks - 1) * tc::BK) + 15) / 16;
         bp.B = B; bp.T = T; bp.t_tiles = (T + tc::BM - 1) / tc::BM;
-        bp.lens = lens_T; bp.h16 = h16; bp.skip = sk; bp.skip_set = (i == 0); bp.scale = rs;
+        bp.lens = lens_T; bp.skip = sk; bp.skip_set = (i == 0); bp.scale = rs;
         bp.skip16 = (i == nb - 1) ? s16 : nullptr;
         static bool attrb[64] = {false};
         if (!attrb[h->device & 63]) {
@@ -1193,6 +1200,8 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
         tc::tc_block_kernel<<<(int)std::min<long long>(tiles, h->sm_count), tc::NUM_THREADS, tc::BLK_SMEM, st>>>(bp);
         lx.check();
         lx.end();
+        std::swap(h16, h16b);          // the block's output is the next block's input
+        std::swap(tm_h, tm_hb);
         continue;
       }
       if (use_tc) {

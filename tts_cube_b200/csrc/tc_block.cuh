@@ -2,7 +2,8 @@
 //     f|g = W1 . [h(t-2d), h(t-d), h(t), c(t)]      GEMM1  [128 rows x 512]   K = 3*128 + 80
 //     o   = tanh(f) * sigmoid(g)                     stays ON CHIP (TMEM -> registers -> swizzled smem A tiles)
 //     r|s = W2 . o                                   GEMM2  [128 rows x 256]   K = 256
-//     h   = (h + r) * sqrt(.5)  (in place, fp16 planes),   skip (+)= s  (fp32)
+//     h'  = (h + r) * sqrt(.5)  (fp16 planes, PING-PONG buffers: other tiles still read h through their taps),
+//     skip (+)= s  (fp32)
 // The unfused pair (tc_conv_kernel GATE + RESSKIP) writes o (1.8 GB per block at B=8 x 10 s) to HBM and reads it
 // back, and its tensor-bound half (gate) and HBM-bound half (res/skip) run back to back; here o never leaves the
 // SM and the residual/skip traffic of tile i hides under the MMAs of tile i+1.
@@ -35,7 +36,10 @@ struct BlockParams {
   int h_chunks, c_chunks, c_last_ksteps;   // K chunks per tap of h (4), of c (3), K steps in c's last chunk (1)
   int B, T, t_tiles;
   const int* lens;
-  __half* h16; float* skip; int skip_set; __half* skip16; float scale;
+  const __half* h_in16;          // residual stream of the block INPUT (same tensor tmH maps; other tiles' gate taps read it,
+                                 // so it must not be updated in place: the unfused pair had a kernel boundary in between)
+  __half* h_out16;               // residual stream of the block OUTPUT (ping-pong buffer)
+  float* skip; int skip_set; __half* skip16; float scale;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_constant__ BlockParams p) {
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
       // pull this tile's residual rows / skip columns into L2 while the MMAs run
       if (in_range) {
         if (grp < 2) {
-          const __half* h0 = p.h16 + ((size_t)b * p.T + t) * 128 + grp * 64;
+          const __half* h0 = p.h_in16 + ((size_t)b * p.T + t) * 128 + grp * 64;
           prefetch_l2(h0);
           prefetch_l2(h0 + (size_t)p.B * p.T * 128);
         } else if (!p.skip_set && (lane & 7) == 0) {
@@ -222,21 +226,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
         const int rg = nt == 0 ? r0 : r1;
         mbar_wait(&acc_full[rg], full_ph[rg] & 1);
         ++full_ph[rg];
-        // the o buffer is free once GEMM2 has consumed the previous half (first half ever: passes at once)
-        mbar_wait(o_free, (ofree_ph & 1) ^ 1);
-        ++ofree_ph;
         tc_fence_after();
         const uint32_t taddr = tmem_base + rg * BN + ((uint32_t)(q * 32) << 16);
         const float2* sb = sb1 + nt * 256;
         // this warp: output channels [32*grp, +32) of this n-tile = K chunk `grp` of the o half
         uint8_t* otile = o_smem + grp * 2 * A_TILE_BYTES;
+        uint32_t hi2[2][8], lo2[2][8];
 #pragma unroll
-        for (int cc = 0; cc < 32; cc += 16) {
+        for (int ci = 0; ci < 2; ++ci) {
+          const int cc = ci * 16;
           uint32_t f[16], g[16];
           tmem_ld16(taddr + grp * 32 + cc, f);
           tmem_ld16(taddr + 128 + grp * 32 + cc, g);
           tmem_ld_wait();
-          uint32_t hi2[8], lo2[8];
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
             float o[2];
@@ -248,21 +250,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
               const float E1 = ex2_fast(a), E2 = ex2_fast(e);
               o[u] = valid ? (E1 - 1.f) * rcp_fast((E1 + 1.f) * (1.f + E2)) : 0.f;
             }
-            split16x2(o[0], o[1], hi2[j >> 1], lo2[j >> 1]);
+            split16x2(o[0], o[1], hi2[ci][j >> 1], lo2[ci][j >> 1]);
           }
-          // K-major SWIZZLE_64B A tile [128 rows][32 ch]: 16-byte piece c16 of row r lives at piece c16 ^ ((r>>1)&3)
+        }
+        // the accumulator region is drained: hand it back before waiting for the o buffer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_free[rg]);
+        // the o buffer is free once GEMM2 has consumed the previous half (first half ever: passes at once)
+        mbar_wait(o_free, (ofree_ph & 1) ^ 1);
+        ++ofree_ph;
+        // K-major SWIZZLE_64B A tile [128 rows][32 ch]: 16-byte piece c16 of row r lives at piece c16 ^ ((r>>1)&3)
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
 #pragma unroll
           for (int v = 0; v < 2; ++v) {
-            const int c16 = (cc >> 3) + v;
+            const int c16 = ci * 2 + v;
             const uint32_t off = row * 64 + ((c16 ^ ((row >> 1) & 3)) << 4);
-            *reinterpret_cast<uint4*>(otile + off) = make_uint4(hi2[4 * v], hi2[4 * v + 1], hi2[4 * v + 2], hi2[4 * v + 3]);
-            *reinterpret_cast<uint4*>(otile + A_TILE_BYTES + off) = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
+            *reinterpret_cast<uint4*>(otile + off) = make_uint4(hi2[ci][4 * v], hi2[ci][4 * v + 1], hi2[ci][4 * v + 2], hi2[ci][4 * v + 3]);
+            *reinterpret_cast<uint4*>(otile + A_TILE_BYTES + off) = make_uint4(lo2[ci][4 * v], lo2[ci][4 * v + 1], lo2[ci][4 * v + 2], lo2[ci][4 * v + 3]);
           }
         }
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        tc_fence_before();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(o_full); mbar_arrive(&acc_free[rg]); }
+        if (lane == 0) mbar_arrive(o_full);
       }
       // ---------------- res/skip epilogue (GEMM2 result in region r0) ----------------
       mbar_wait(&acc_full[r0], full_ph[r0] & 1);
@@ -272,7 +283,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
         const uint32_t taddr = tmem_base + r0 * BN + ((uint32_t)(q * 32) << 16);
         if (grp < 2) {   // cols [0,128): residual stream in place; this warp: channels [64*grp, +64)
           const size_t plane = (size_t)p.B * p.T * 128;
-          __half* hrow = p.h16 + ((size_t)b * p.T + t) * 128;
+          const __half* hrow = p.h_in16 + ((size_t)b * p.T + t) * 128;
+          __half* orow = p.h_out16 + ((size_t)b * p.T + t) * 128;
 #pragma unroll
           for (int cc = grp * 64; cc < grp * 64 + 64; cc += 16) {
             uint32_t r[16];
@@ -303,12 +315,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
             if (in_range) {
 #pragma unroll
               for (int v = 0; v < 2; ++v) {
-                reinterpret_cast<uint4*>(hrow + cc)[v] = make_uint4(hi2[4 * v], hi2[4 * v + 1], hi2[4 * v + 2], hi2[4 * v + 3]);
-                reinterpret_cast<uint4*>(hrow + plane + cc)[v] = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
+                reinterpret_cast<uint4*>(orow + cc)[v] = make_uint4(hi2[4 * v], hi2[4 * v + 1], hi2[4 * v + 2], hi2[4 * v + 3]);
+                reinterpret_cast<uint4*>(orow + plane + cc)[v] = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
               }
             }
           }
-        } else {         // cols [128,256): skip accumulator; this warp: skip channels [64*(grp-2), +64)
+        } else {         // cols [128,256): skip accumulator fp32 [B][128][T] (lanes = consecutive t: one 128-B line per
+                         // column and warp - measured faster than a channels-last row per thread); channels [64*(grp-2), +64)
           float* sp0 = p.skip + (size_t)b * 128 * p.T + t;
 #pragma unroll
           for (int cc = (grp - 2) * 64; cc < (grp - 2) * 64 + 64; cc += 16) {
