@@ -22,7 +22,7 @@
 
 #define CUBE_VERSION "0.1.0"
 #ifndef CUBE_FUSED_DEFAULT
-#define CUBE_FUSED_DEFAULT false
+#define CUBE_FUSED_DEFAULT true
 #endif
 
 namespace cube {

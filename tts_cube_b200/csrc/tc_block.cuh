@@ -42,6 +42,7 @@ struct BlockParams {
   float* skip; int skip_set; __half* skip16; float scale;
 };
 
+// 18 warps: the SM sub-partitions hold 5,5,4,4 of them, so 16384/5 -> 96 registers per thread is the hardware cap
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_constant__ BlockParams p) {
   constexpr int BN = 256;
   constexpr int B_BYTES = BN * BK * 2;             // 16 KB per plane
@@ -280,15 +281,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
       ++full_ph[r0];
       tc_fence_after();
       {
-        const uint32_t taddr = tmem_base + r0 * BN + ((uint32_t)(q * 32) << 16);
-        if (grp < 2) {   // cols [0,128): residual stream in place; this warp: channels [64*grp, +64)
+        // Drain this warp's 64 accumulator columns into registers and hand the TMEM region back at once: the slow
+        // part below (global read-modify-write of the residual / skip streams) then no longer sits between this
+        // tile's GEMM2 and the next tile's GEMM1 that reuses the region.
+        const uint32_t taddr = tmem_base + r0 * BN + ((uint32_t)(q * 32) << 16) + (grp < 2 ? grp * 64 : 128 + (grp - 2) * 64);
+        uint32_t racc[64];
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) tmem_ld16(taddr + ci * 16, *reinterpret_cast<uint32_t(*)[16]>(&racc[ci * 16]));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_free[r0]);
+        if (grp < 2) {   // cols [0,128): residual stream h_in -> h_out; this warp: channels [64*grp, +64)
           const size_t plane = (size_t)p.B * p.T * 128;
           const __half* hrow = p.h_in16 + ((size_t)b * p.T + t) * 128;
           __half* orow = p.h_out16 + ((size_t)b * p.T + t) * 128;
 #pragma unroll
-          for (int cc = grp * 64; cc < grp * 64 + 64; cc += 16) {
-            uint32_t r[16];
-            tmem_ld16(taddr + cc, r);
+          for (int ci = 0; ci < 4; ++ci) {
+            const int cc = grp * 64 + ci * 16;
             uint4 hv[2], lv[2];
             if (in_range) {
 #pragma unroll
@@ -299,7 +309,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
             } else {
               hv[0] = hv[1] = lv[0] = lv[1] = make_uint4(0, 0, 0, 0);
             }
-            tmem_ld_wait();
             const uint32_t* hp = reinterpret_cast<const uint32_t*>(hv);
             const uint32_t* lp = reinterpret_cast<const uint32_t*>(lv);
             uint32_t hi2[8], lo2[8];
@@ -307,7 +316,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
             for (int j = 0; j < 16; j += 2) {
               const float2 s0 = sb2[cc + j], s1 = sb2[cc + j + 1];
               const float2 oh = unpack_h2(hp[j >> 1]), ol = unpack_h2(lp[j >> 1]);
-              const float v0 = fmaf(__uint_as_float(r[j]), s0.x, s0.y), v1 = fmaf(__uint_as_float(r[j + 1]), s1.x, s1.y);
+              const float v0 = fmaf(__uint_as_float(racc[ci * 16 + j]), s0.x, s0.y), v1 = fmaf(__uint_as_float(racc[ci * 16 + j + 1]), s1.x, s1.y);
               const float n0 = valid ? ((oh.x + ol.x) + v0) * p.scale : 0.f;
               const float n1 = valid ? ((oh.y + ol.y) + v1) * p.scale : 0.f;
               split16x2(n0, n1, hi2[j >> 1], lo2[j >> 1]);
@@ -324,10 +333,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
                          // column and warp - measured faster than a channels-last row per thread); channels [64*(grp-2), +64)
           float* sp0 = p.skip + (size_t)b * 128 * p.T + t;
 #pragma unroll
-          for (int cc = (grp - 2) * 64; cc < (grp - 2) * 64 + 64; cc += 16) {
-            uint32_t r[16];
+          for (int ci = 0; ci < 4; ++ci) {
+            const int cc = (grp - 2) * 64 + ci * 16;
             float old[16];
-            tmem_ld16(taddr + 128 + cc, r);
             if (in_range && !p.skip_set) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) old[j] = __ldcs(sp0 + (size_t)(cc + j) * p.T);
@@ -335,14 +343,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
 #pragma unroll
               for (int j = 0; j < 16; ++j) old[j] = 0.f;
             }
-            tmem_ld_wait();
             if (p.skip16) {
               uint32_t hi2[8], lo2[8];
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
                 const float2 s0 = sb2[128 + cc + j], s1 = sb2[128 + cc + j + 1];
-                const float y0 = old[j] + fmaf(__uint_as_float(r[j]), s0.x, s0.y);
-                const float y1 = old[j + 1] + fmaf(__uint_as_float(r[j + 1]), s1.x, s1.y);
+                const float y0 = old[j] + fmaf(__uint_as_float(racc[ci * 16 + j]), s0.x, s0.y);
+                const float y1 = old[j + 1] + fmaf(__uint_as_float(racc[ci * 16 + j + 1]), s1.x, s1.y);
                 split16x2(valid ? fmaxf(y0, 0.f) : 0.f, valid ? fmaxf(y1, 0.f) : 0.f, hi2[j >> 1], lo2[j >> 1]);
               }
               if (in_range) {
@@ -358,16 +365,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const float2 s2 = sb2[128 + cc + j];
-                const float y = old[j] + fmaf(__uint_as_float(r[j]), s2.x, s2.y);
+                const float y = old[j] + fmaf(__uint_as_float(racc[ci * 16 + j]), s2.x, s2.y);
                 __stcs(sp0 + (size_t)(cc + j) * p.T, valid ? y : 0.f);
               }
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_free[r0]);
     }
   }
   tc_fence_before();
