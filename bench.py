@@ -38,8 +38,11 @@ WORKLOADS = {
 # algorithmic work per output sample of the dominant kernel (DESIGN.md "Measurement")
 GATE_FLOPS = 2.0 * (2 * 256 * 128 * 3 + 2 * 256 * 80)     # gated dilated conv + conditioning 1x1
 GATE_BYTES = 4.0 * (128 + 80 + 256)                        # read h, read c_up, write o (fp32)
+BLOCK_FLOPS = GATE_FLOPS + 2.0 * (256 * 256)               # + res/skip 1x1 256 -> 128+128 (fused block kernel)
+BLOCK_BYTES = 4.0 * (128 + 80 + 128 + 128 + 128)           # read h, c_up, skip; write h', skip (fp32 equivalents)
 HIFI_FLOPS_PER_SAMPLE = 1022.2e3                           # SURVEY 8(d), neb-noft rates
 HIFI_BYTES_PER_SAMPLE = 9021.0
+FUSED_TRAFFIC = 4.16e9                                     # dram read + write of one tc_block_kernel launch (ncu)
 PWN_FLOPS_PER_SAMPLE = 25.63e6
 PWN_BYTES_PER_SAMPLE = 103609.0
 
@@ -375,21 +378,25 @@ def main():
     d2h = out_host.numel() * 4
     # ---- roofline of the dominant kernel (device time of its launches inside the last timed step) ----
     if arch == "student":
-        dom = "gate"
+        fused = prof.get("block_fused", 0.0) > 0.0
+        dom = "block_fused" if fused else "gate"
         nlaunch = sum(int(weights[0][k].shape[0] > 0) for k in weights[0] if k.endswith("filter_conv.conv.bias"))
         dom_ms = prof.get(dom, 0.0)
-        flops_launch = GATE_FLOPS * samples_per_step
+        flops_launch = (BLOCK_FLOPS if fused else GATE_FLOPS) * samples_per_step
         ach = flops_launch * nlaunch / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else None
         roof = {"kernel": "conv_tile_kernel<8,8,8,1> EPI_GATE (gated dilated conv k3 128->2x256 + conditioning 1x1 80->2x256, fp32 FFMA2)" if math == 0
-                else "tc::tc_conv_kernel TC_EPI_GATE (same layer on tcgen05: UMMA 128x256x16 f16, split-fp16 x3, TMA taps)",
+                else ("tc::tc_block_kernel (whole residual block: gated dilated conv + conditioning 1x1 -> o kept in smem -> res/skip 1x1; "
+                      "tcgen05 UMMA 128x256x16 f16, split-fp16 x3, TMA taps)" if fused else
+                      "tc::tc_conv_kernel TC_EPI_GATE (same layer on tcgen05: UMMA 128x256x16 f16, split-fp16 x3, TMA taps)"),
                 "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                 "frac": (ach / pk["tf_sust"]) if ach else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, round 1
                 # (profiles/r1_ncu_full_tc_conv.md: 1.52 GB + 1.79 GB); only valid for the default geometry
-                "traffic": 3.31e9 if (math == 1 and B == 8 and F == 862) else None,
-                "traffic_source": "profiles/r1_ncu_full_tc_conv.md (ncu --set full, gate launch)",
+                "traffic": (FUSED_TRAFFIC if fused else 3.31e9) if (math == 1 and B == 8 and F == 862) else None,
+                "traffic_source": ("profiles/r1_ncu_full_tc_block.md (ncu --set full, one tc_block_kernel launch)" if fused else
+                                   "profiles/r1_ncu_full_tc_conv.md (ncu --set full, gate launch)"),
                 "launches_per_step": nlaunch, "avg_launch_ms": dom_ms / max(1, nlaunch),
-                "algorithmic_flops_per_launch": flops_launch, "algorithmic_bytes_per_launch": GATE_BYTES * samples_per_step,
+                "algorithmic_flops_per_launch": flops_launch, "algorithmic_bytes_per_launch": (BLOCK_BYTES if fused else GATE_BYTES) * samples_per_step,
                 "share_of_step": dom_ms / (ms / args.steps) if ms > 0 else None,
                 "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
                 "math": "fp32 FFMA (no tensor cores)" if math == 0 else "tcgen05 split-fp16 x3"}

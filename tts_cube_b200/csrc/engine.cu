@@ -846,6 +846,34 @@ static bool use_win(const cube_voc* h) {
   return h->cfg.arch == CUBE_VOC_HIFIGAN;
 }
 
+// CUBE_BLOCK_STATS=1: run the instrumented fused block kernel and print CTA 0's wait cycles after each forward
+static bool block_stats_on() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CUBE_BLOCK_STATS"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+static unsigned long long* block_stats_buf() {
+  static unsigned long long* buf = nullptr;
+  if (!buf) { cudaMalloc(&buf, 32 * sizeof(unsigned long long)); cudaMemset(buf, 0, 32 * sizeof(unsigned long long)); }
+  return buf;
+}
+static void block_stats_dump(cudaStream_t st) {
+  if (!block_stats_on()) return;
+  unsigned long long v[32];
+  cudaStreamSynchronize(st);
+  cudaMemcpy(v, block_stats_buf(), sizeof(v), cudaMemcpyDeviceToHost);
+  cudaMemset(block_stats_buf(), 0, sizeof(v));
+  static const char* names[27] = {"prod.wait_empty_g1", "prod.wait_empty_g2", "prod.total",
+    "mma.wait_accfree_g1a", "mma.wait_accfree_g1b", "mma.wait_full_g1", "mma.wait_accfree_g2", "mma.wait_ofull_kh0", "mma.wait_ofull_kh1",
+    "mma.wait_full_g2", "mma.total",
+    "epiR.wait_accfull_nt0", "epiR.wait_accfull_nt1", "epiR.wait_ofree_nt0", "epiR.wait_ofree_nt1", "epiR.wait_accfull_rs", "epiR.gate_math",
+    "epiR.res_rmw", "epiR.skip_rmw",
+    "epiS.wait_accfull_nt0", "epiS.wait_accfull_nt1", "epiS.wait_ofree_nt0", "epiS.wait_ofree_nt1", "epiS.wait_accfull_rs", "epiS.gate_math",
+    "epiS.res_rmw", "epiS.skip_rmw"};
+  fprintf(stderr, "[cube block stats] CTA 0, cycles summed over the forward:\n");
+  for (int i = 0; i < 27; ++i) fprintf(stderr, "  %-24s %14llu  (%.1f %% of mma.total)\n", names[i], v[i], 100.0 * (double)v[i] / (double)(v[10] ? v[10] : 1));
+}
+
 // fused residual-block kernel (tc_block.cuh) for the student: CUBE_TC_FUSED=0/1 overrides the default
 static bool use_fused() {
   static int v = -2;
@@ -1193,11 +1221,18 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
         bp.skip16 = (i == nb - 1) ? s16 : nullptr;
         static bool attrb[64] = {false};
         if (!attrb[h->device & 63]) {
-          CU_TRY(cudaFuncSetAttribute(tc::tc_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::BLK_SMEM));
+          CU_TRY(cudaFuncSetAttribute(tc::tc_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::BLK_SMEM));
+          CU_TRY(cudaFuncSetAttribute(tc::tc_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::BLK_SMEM));
           attrb[h->device & 63] = true;
         }
         const long long tiles = (long long)bp.t_tiles * B;
-        tc::tc_block_kernel<<<(int)std::min<long long>(tiles, h->sm_count), tc::NUM_THREADS, tc::BLK_SMEM, st>>>(bp);
+        const int grid = (int)std::min<long long>(tiles, h->sm_count);
+        if (block_stats_on()) {   // instrumented build: wait cycles of CTA 0 per barrier, printed by block_stats_dump()
+          bp.stats = block_stats_buf();
+          tc::tc_block_kernel<true><<<grid, tc::NUM_THREADS, tc::BLK_SMEM, st>>>(bp);
+        } else {
+          tc::tc_block_kernel<false><<<grid, tc::NUM_THREADS, tc::BLK_SMEM, st>>>(bp);
+        }
         lx.check();
         lx.end();
         std::swap(h16, h16b);          // the block's output is the next block's input
@@ -1296,6 +1331,7 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
     lx.check();
     lx.end();
   }
+  block_stats_dump(st);
   return lx.err;
 }
 

@@ -40,10 +40,26 @@ struct BlockParams {
                                  // so it must not be updated in place: the unfused pair had a kernel boundary in between)
   __half* h_out16;               // residual stream of the block OUTPUT (ping-pong buffer)
   float* skip; int skip_set; __half* skip16; float scale;
+  unsigned long long* stats;     // STATS build only: wait-cycle counters of CTA 0 (CUBE_BLOCK_STATS=1), 24 slots
 };
 
+// wait on an mbarrier, charging the cycles to a counter slot in the instrumented build
+#define BLK_WAIT(bar, par, slot)                                   \
+  do {                                                             \
+    if (STATS) {                                                   \
+      const long long _t0 = clock64();                             \
+      mbar_wait(bar, par);                                         \
+      st_acc[slot] += clock64() - _t0;                             \
+    } else {                                                       \
+      mbar_wait(bar, par);                                         \
+    }                                                              \
+  } while (0)
+
 // 18 warps: the SM sub-partitions hold 5,5,4,4 of them, so 16384/5 -> 96 registers per thread is the hardware cap
+template <bool STATS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_constant__ BlockParams p) {
+  long long st_acc[STATS ? 8 : 1] = {0};
+  const long long st_begin = STATS ? clock64() : 0;
   constexpr int BN = 256;
   constexpr int B_BYTES = BN * BK * 2;             // 16 KB per plane
   extern __shared__ uint8_t smem_raw[];
@@ -103,7 +119,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
             const int ncc = cond ? p.c_chunks : p.h_chunks;
             for (int cc = 0; cc < ncc; ++cc, ++chunk, ++it) {
               const int st = it % BLK_STAGES;
-              mbar_wait(&empty[st], ((it / BLK_STAGES) & 1) ^ 1);
+              BLK_WAIT(&empty[st], ((it / BLK_STAGES) & 1) ^ 1, 0);
               uint8_t* sb = smem + st * BLK_STAGE_BYTES;
               mbar_expect_tx(&full[st], BLK_STAGE_BYTES);
               const CUtensorMap* tm = cond ? &p.tmC : &p.tmH;
@@ -117,13 +133,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
         }
         for (int ch = 0; ch < 8; ++ch, ++it) {                 // GEMM2: weights only (its A operand is o, on chip)
           const int st = it % BLK_STAGES;
-          mbar_wait(&empty[st], ((it / BLK_STAGES) & 1) ^ 1);
+          BLK_WAIT(&empty[st], ((it / BLK_STAGES) & 1) ^ 1, 1);
           uint8_t* sb = smem + st * BLK_STAGE_BYTES;
           mbar_expect_tx(&full[st], 2 * B_BYTES);
           const __half* wc = p.W2 + (size_t)ch * 2 * (BN * BK);
           bulk_load(sb + 2 * A_TILE_BYTES, wc, B_BYTES, &full[st]);
           bulk_load(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, &full[st]);
         }
+      }
+      if (STATS && p.stats && blockIdx.x == 0) {
+        atomicAdd(p.stats + 0, (unsigned long long)st_acc[0]);
+        atomicAdd(p.stats + 1, (unsigned long long)st_acc[1]);
+        atomicAdd(p.stats + 2, (unsigned long long)(clock64() - st_begin));
       }
     }
   } else if (warp == 1) {
@@ -138,7 +159,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
         for (int nt = 0; nt < 2; ++nt) {
           const int rg = nt == 0 ? r0 : r1;
           // the region must have been drained by its previous user (first use of each region: passes at once)
-          mbar_wait(&acc_free[rg], (free_ph[rg] & 1) ^ 1);
+          BLK_WAIT(&acc_free[rg], (free_ph[rg] & 1) ^ 1, nt);
           ++free_ph[rg];
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + rg * BN;
@@ -148,7 +169,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
             const int ncc = cond ? p.c_chunks : p.h_chunks;
             for (int cc = 0; cc < ncc; ++cc, ++it) {
               const int st = it % BLK_STAGES;
-              mbar_wait(&full[st], (it / BLK_STAGES) & 1);
+              BLK_WAIT(&full[st], (it / BLK_STAGES) & 1, 2);
               tc_fence_after();
               const uint32_t a_hi = smem_u32(smem + st * BLK_STAGE_BYTES), a_lo = a_hi + A_TILE_BYTES;
               const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + B_BYTES;
@@ -167,17 +188,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
         }
         // GEMM2 into r0 (drained by the gate epilogue of n-tile 0): K half kh uses the o half the epilogue staged
         {
-          mbar_wait(&acc_free[r0], (free_ph[r0] & 1) ^ 1);
+          BLK_WAIT(&acc_free[r0], (free_ph[r0] & 1) ^ 1, 3);
           ++free_ph[r0];
           const uint32_t d_tmem = tmem_base + r0 * BN;
           uint32_t accumulate = 0;
           for (int kh = 0; kh < 2; ++kh) {
-            mbar_wait(o_full, ofull_ph & 1);
+            BLK_WAIT(o_full, ofull_ph & 1, 4 + kh);
             ++ofull_ph;
             tc_fence_after();
             for (int c4 = 0; c4 < 4; ++c4, ++it) {
               const int st = it % BLK_STAGES;
-              mbar_wait(&full[st], (it / BLK_STAGES) & 1);
+              BLK_WAIT(&full[st], (it / BLK_STAGES) & 1, 6);
               tc_fence_after();
               const uint32_t a_hi = smem_u32(o_smem + c4 * 2 * A_TILE_BYTES), a_lo = a_hi + A_TILE_BYTES;
               const uint32_t b_hi = smem_u32(smem + st * BLK_STAGE_BYTES) + 2 * A_TILE_BYTES, b_lo = b_hi + B_BYTES;
@@ -194,6 +215,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
           }
           umma_commit(&acc_full[r0]);     // r|s accumulator complete
         }
+      }
+      if (STATS && p.stats && blockIdx.x == 0) {
+        for (int i = 0; i < 7; ++i) atomicAdd(p.stats + 3 + i, (unsigned long long)st_acc[i]);
+        atomicAdd(p.stats + 10, (unsigned long long)(clock64() - st_begin));
       }
     }
   } else {
@@ -225,8 +250,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
       // ---------------- gate epilogue of n-tile 0 (region r0) and n-tile 1 (region r1) ----------------
       for (int nt = 0; nt < 2; ++nt) {
         const int rg = nt == 0 ? r0 : r1;
-        mbar_wait(&acc_full[rg], full_ph[rg] & 1);
+        BLK_WAIT(&acc_full[rg], full_ph[rg] & 1, nt);
         ++full_ph[rg];
+        const long long g_t0 = STATS ? clock64() : 0;
         tc_fence_after();
         const uint32_t taddr = tmem_base + rg * BN + ((uint32_t)(q * 32) << 16);
         const float2* sb = sb1 + nt * 256;
@@ -259,7 +285,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_free[rg]);
         // the o buffer is free once GEMM2 has consumed the previous half (first half ever: passes at once)
-        mbar_wait(o_free, (ofree_ph & 1) ^ 1);
+        if (STATS) st_acc[5] += clock64() - g_t0;       // gate math (TMEM load .. region handed back)
+        BLK_WAIT(o_free, (ofree_ph & 1) ^ 1, 2 + nt);
         ++ofree_ph;
         // K-major SWIZZLE_64B A tile [128 rows][32 ch]: 16-byte piece c16 of row r lives at piece c16 ^ ((r>>1)&3)
 #pragma unroll
@@ -277,101 +304,121 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
         if (lane == 0) mbar_arrive(o_full);
       }
       // ---------------- res/skip epilogue (GEMM2 result in region r0) ----------------
-      mbar_wait(&acc_full[r0], full_ph[r0] & 1);
-      ++full_ph[r0];
-      tc_fence_after();
-      {
-        // Drain this warp's 64 accumulator columns into registers and hand the TMEM region back at once: the slow
-        // part below (global read-modify-write of the residual / skip streams) then no longer sits between this
-        // tile's GEMM2 and the next tile's GEMM1 that reuses the region.
-        const uint32_t taddr = tmem_base + r0 * BN + ((uint32_t)(q * 32) << 16) + (grp < 2 ? grp * 64 : 128 + (grp - 2) * 64);
-        uint32_t racc[64];
+      // The global reads of this tile's residual rows / skip columns do not depend on GEMM2: they are all issued
+      // BEFORE waiting for its accumulator, so their latency (several thousand cycles next to the TMA stream) hides
+      // behind GEMM2's second K half instead of sitting, four dependent batches deep, between this tile's GEMM2 and
+      // the gate epilogues of the next tile (measured with CUBE_BLOCK_STATS=1: that chain, not the MMAs, set the pace).
+      const uint32_t taddr_rs = tmem_base + r0 * BN + ((uint32_t)(q * 32) << 16) + (grp < 2 ? grp * 64 : 128 + (grp - 2) * 64);
+      long long r_t0 = 0;
+      if (grp < 2) {   // cols [0,128): residual stream h_in -> h_out; this warp: channels [64*grp, +64)
+        const size_t plane = (size_t)p.B * p.T * 128;
+        const __half* hrow = p.h_in16 + ((size_t)b * p.T + t) * 128 + grp * 64;
+        __half* orow = p.h_out16 + ((size_t)b * p.T + t) * 128 + grp * 64;
+        uint4 hreg[16];            // [ci][hi piece 0, hi piece 1, lo piece 0, lo piece 1]
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci) tmem_ld16(taddr + ci * 16, *reinterpret_cast<uint32_t(*)[16]>(&racc[ci * 16]));
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_free[r0]);
-        if (grp < 2) {   // cols [0,128): residual stream h_in -> h_out; this warp: channels [64*grp, +64)
-          const size_t plane = (size_t)p.B * p.T * 128;
-          const __half* hrow = p.h_in16 + ((size_t)b * p.T + t) * 128;
-          __half* orow = p.h_out16 + ((size_t)b * p.T + t) * 128;
+        for (int ci = 0; ci < 4; ++ci) {
+          if (in_range) {
+            hreg[ci * 4 + 0] = reinterpret_cast<const uint4*>(hrow + ci * 16)[0];
+            hreg[ci * 4 + 1] = reinterpret_cast<const uint4*>(hrow + ci * 16)[1];
+            hreg[ci * 4 + 2] = reinterpret_cast<const uint4*>(hrow + plane + ci * 16)[0];
+            hreg[ci * 4 + 3] = reinterpret_cast<const uint4*>(hrow + plane + ci * 16)[1];
+          } else {
+            hreg[ci * 4 + 0] = hreg[ci * 4 + 1] = hreg[ci * 4 + 2] = hreg[ci * 4 + 3] = make_uint4(0, 0, 0, 0);
+          }
+        }
+        BLK_WAIT(&acc_full[r0], full_ph[r0] & 1, 4);
+        if (STATS) r_t0 = clock64();
+        tc_fence_after();
 #pragma unroll
-          for (int ci = 0; ci < 4; ++ci) {
-            const int cc = grp * 64 + ci * 16;
-            uint4 hv[2], lv[2];
-            if (in_range) {
+        for (int ci = 0; ci < 4; ++ci) {
+          const int cc = grp * 64 + ci * 16;
+          uint32_t racc[16];
+          tmem_ld16(taddr_rs + ci * 16, racc);
+          tmem_ld_wait();
+          if (ci == 3) {           // last TMEM read of this warp: hand the region back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_free[r0]);
+          }
+          const uint32_t* hp = reinterpret_cast<const uint32_t*>(&hreg[ci * 4]);
+          const uint32_t* lp = reinterpret_cast<const uint32_t*>(&hreg[ci * 4 + 2]);
+          uint32_t hi2[8], lo2[8];
 #pragma unroll
-              for (int v = 0; v < 2; ++v) {
-                hv[v] = reinterpret_cast<const uint4*>(hrow + cc)[v];
-                lv[v] = reinterpret_cast<const uint4*>(hrow + plane + cc)[v];
-              }
-            } else {
-              hv[0] = hv[1] = lv[0] = lv[1] = make_uint4(0, 0, 0, 0);
+          for (int j = 0; j < 16; j += 2) {
+            const float2 s0 = sb2[cc + j], s1 = sb2[cc + j + 1];
+            const float2 oh = unpack_h2(hp[j >> 1]), ol = unpack_h2(lp[j >> 1]);
+            const float v0 = fmaf(__uint_as_float(racc[j]), s0.x, s0.y), v1 = fmaf(__uint_as_float(racc[j + 1]), s1.x, s1.y);
+            const float n0 = valid ? ((oh.x + ol.x) + v0) * p.scale : 0.f;
+            const float n1 = valid ? ((oh.y + ol.y) + v1) * p.scale : 0.f;
+            split16x2(n0, n1, hi2[j >> 1], lo2[j >> 1]);
+          }
+          if (in_range) {
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              reinterpret_cast<uint4*>(orow + ci * 16)[v] = make_uint4(hi2[4 * v], hi2[4 * v + 1], hi2[4 * v + 2], hi2[4 * v + 3]);
+              reinterpret_cast<uint4*>(orow + plane + ci * 16)[v] = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
             }
-            const uint32_t* hp = reinterpret_cast<const uint32_t*>(hv);
-            const uint32_t* lp = reinterpret_cast<const uint32_t*>(lv);
+          }
+        }
+      } else {         // cols [128,256): skip accumulator fp32 [B][128][T] (lanes = consecutive t: one 128-B line per
+                       // column and warp - measured faster than a channels-last row per thread); channels [64*(grp-2), +64)
+        float* sp0 = p.skip + ((size_t)b * 128 + (grp - 2) * 64) * p.T + t;
+        float old[64];
+        if (in_range && !p.skip_set) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) old[j] = __ldcs(sp0 + (size_t)j * p.T);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) old[j] = 0.f;
+        }
+        BLK_WAIT(&acc_full[r0], full_ph[r0] & 1, 4);
+        if (STATS) r_t0 = clock64();
+        tc_fence_after();
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int cc = (grp - 2) * 64 + ci * 16;
+          uint32_t racc[16];
+          tmem_ld16(taddr_rs + ci * 16, racc);
+          tmem_ld_wait();
+          if (ci == 3) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_free[r0]);
+          }
+          if (p.skip16) {
             uint32_t hi2[8], lo2[8];
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              const float2 s0 = sb2[cc + j], s1 = sb2[cc + j + 1];
-              const float2 oh = unpack_h2(hp[j >> 1]), ol = unpack_h2(lp[j >> 1]);
-              const float v0 = fmaf(__uint_as_float(racc[ci * 16 + j]), s0.x, s0.y), v1 = fmaf(__uint_as_float(racc[ci * 16 + j + 1]), s1.x, s1.y);
-              const float n0 = valid ? ((oh.x + ol.x) + v0) * p.scale : 0.f;
-              const float n1 = valid ? ((oh.y + ol.y) + v1) * p.scale : 0.f;
-              split16x2(n0, n1, hi2[j >> 1], lo2[j >> 1]);
+              const float2 s0 = sb2[128 + cc + j], s1 = sb2[128 + cc + j + 1];
+              const float y0 = old[ci * 16 + j] + fmaf(__uint_as_float(racc[j]), s0.x, s0.y);
+              const float y1 = old[ci * 16 + j + 1] + fmaf(__uint_as_float(racc[j + 1]), s1.x, s1.y);
+              split16x2(valid ? fmaxf(y0, 0.f) : 0.f, valid ? fmaxf(y1, 0.f) : 0.f, hi2[j >> 1], lo2[j >> 1]);
             }
             if (in_range) {
+              __half* srow = p.skip16 + ((size_t)b * p.T + t) * 128 + cc;
+              const size_t splane = (size_t)p.B * p.T * 128;
 #pragma unroll
               for (int v = 0; v < 2; ++v) {
-                reinterpret_cast<uint4*>(orow + cc)[v] = make_uint4(hi2[4 * v], hi2[4 * v + 1], hi2[4 * v + 2], hi2[4 * v + 3]);
-                reinterpret_cast<uint4*>(orow + plane + cc)[v] = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
+                reinterpret_cast<uint4*>(srow)[v] = make_uint4(hi2[4 * v], hi2[4 * v + 1], hi2[4 * v + 2], hi2[4 * v + 3]);
+                reinterpret_cast<uint4*>(srow + splane)[v] = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
               }
             }
-          }
-        } else {         // cols [128,256): skip accumulator fp32 [B][128][T] (lanes = consecutive t: one 128-B line per
-                         // column and warp - measured faster than a channels-last row per thread); channels [64*(grp-2), +64)
-          float* sp0 = p.skip + (size_t)b * 128 * p.T + t;
+          } else if (in_range) {
 #pragma unroll
-          for (int ci = 0; ci < 4; ++ci) {
-            const int cc = (grp - 2) * 64 + ci * 16;
-            float old[16];
-            if (in_range && !p.skip_set) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) old[j] = __ldcs(sp0 + (size_t)(cc + j) * p.T);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) old[j] = 0.f;
-            }
-            if (p.skip16) {
-              uint32_t hi2[8], lo2[8];
-#pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                const float2 s0 = sb2[128 + cc + j], s1 = sb2[128 + cc + j + 1];
-                const float y0 = old[j] + fmaf(__uint_as_float(racc[ci * 16 + j]), s0.x, s0.y);
-                const float y1 = old[j + 1] + fmaf(__uint_as_float(racc[ci * 16 + j + 1]), s1.x, s1.y);
-                split16x2(valid ? fmaxf(y0, 0.f) : 0.f, valid ? fmaxf(y1, 0.f) : 0.f, hi2[j >> 1], lo2[j >> 1]);
-              }
-              if (in_range) {
-                __half* srow = p.skip16 + ((size_t)b * p.T + t) * 128 + cc;
-                const size_t splane = (size_t)p.B * p.T * 128;
-#pragma unroll
-                for (int v = 0; v < 2; ++v) {
-                  reinterpret_cast<uint4*>(srow)[v] = make_uint4(hi2[4 * v], hi2[4 * v + 1], hi2[4 * v + 2], hi2[4 * v + 3]);
-                  reinterpret_cast<uint4*>(srow + splane)[v] = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
-                }
-              }
-            } else if (in_range) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float2 s2 = sb2[128 + cc + j];
-                const float y = old[j] + fmaf(__uint_as_float(racc[ci * 16 + j]), s2.x, s2.y);
-                __stcs(sp0 + (size_t)(cc + j) * p.T, valid ? y : 0.f);
-              }
+            for (int j = 0; j < 16; ++j) {
+              const float2 s2 = sb2[128 + cc + j];
+              const float y = old[ci * 16 + j] + fmaf(__uint_as_float(racc[j]), s2.x, s2.y);
+              __stcs(sp0 + (size_t)(ci * 16 + j) * p.T, valid ? y : 0.f);
             }
           }
         }
       }
+      ++full_ph[r0];
+      if (STATS) st_acc[grp < 2 ? 6 : 7] += clock64() - r_t0;   // residual / skip read-modify-write
+    }
+    if (STATS && p.stats && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 10)) {
+      unsigned long long* o = p.stats + (warp == 2 ? 11 : 19);
+      for (int i = 0; i < 8; ++i) atomicAdd(o + i, (unsigned long long)st_acc[i]);
     }
   }
   tc_fence_before();

@@ -225,7 +225,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
       "}" ::"r"(smem_u32(bar)), "r"(rank) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
