@@ -321,7 +321,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
 
 // fp16 planes [2][B][T][C] channels-last -> 3-D tensor map (C, T, 2B), box (64, 128, 1), 128B swizzle,
 // out-of-bounds rows/channels read as zero (that IS the conv zero padding).
-static int make_tmap_hl16(CUtensorMap* tm, const __half* base, int B, int T, int C) {
+static int make_tmap_hl16(CUtensorMap* tm, const __half* base, int B, int T, int C, int box_rows = tc::BM) {
   static PFN_tmapEncodeTiled fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -333,7 +333,7 @@ static int make_tmap_hl16(CUtensorMap* tm, const __half* base, int B, int T, int
   if (C % 8) return fail("channels-last fp16 tensor needs C %% 8 == 0 (got %d)", C);
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)(2 * B)};
   cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2};
-  cuuint32_t box[3] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM, 1};
+  cuuint32_t box[3] = {(cuuint32_t)tc::BK, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   tc::BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -867,9 +867,9 @@ static void block_stats_dump(cudaStream_t st) {
     "mma.wait_accfree_g1a", "mma.wait_accfree_g1b", "mma.wait_full_g1", "mma.wait_accfree_g2", "mma.wait_ofull_kh0", "mma.wait_ofull_kh1",
     "mma.wait_full_g2", "mma.total",
     "epiR.wait_accfull_nt0", "epiR.wait_accfull_nt1", "epiR.wait_ofree_nt0", "epiR.wait_ofree_nt1", "epiR.wait_accfull_rs", "epiR.gate_math",
-    "epiR.res_rmw", "epiR.skip_rmw",
+    "epiR.resskip", "epiR.-",
     "epiS.wait_accfull_nt0", "epiS.wait_accfull_nt1", "epiS.wait_ofree_nt0", "epiS.wait_ofree_nt1", "epiS.wait_accfull_rs", "epiS.gate_math",
-    "epiS.res_rmw", "epiS.skip_rmw"};
+    "epiS.resskip", "epiS.-"};
   fprintf(stderr, "[cube block stats] CTA 0, cycles summed over the forward:\n");
   for (int i = 0; i < 27; ++i) fprintf(stderr, "  %-24s %14llu  (%.1f %% of mma.total)\n", names[i], v[i], 100.0 * (double)v[i] / (double)(v[10] ? v[10] : 1));
 }
@@ -1150,7 +1150,7 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
   const float rs = sqrtf(0.5f);
   const bool use_tc = (c.math == CUBE_MATH_TC_SPLIT16);
   __half *h16 = nullptr, *h16b = nullptr, *o16 = nullptr, *c16 = nullptr, *s16 = nullptr;
-  CUtensorMap tm_h, tm_hb, tm_o, tm_c, tm_s;
+  CUtensorMap tm_h, tm_hb, tm_o, tm_c, tm_s, tm_h32, tm_hb32;
   if (use_tc) {
     float *t1, *t2, *t3, *t4;
     if (ws_get(h, "s16", (size_t)B * T * S, &t4)) return 1;
@@ -1160,13 +1160,14 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
       float* t5;
       if (ws_get(h, "h16b", (size_t)B * T * R, &t5)) return 1;
       h16b = (__half*)t5;
-      if (make_tmap_hl16(&tm_hb, h16b, B, T, R)) return 1;
+      if (make_tmap_hl16(&tm_hb, h16b, B, T, R) || make_tmap_hl16(&tm_hb32, h16b, B, T, R, 32)) return 1;
     }
     // fp16 (hi, lo) planes, channels-last: 2*2 bytes per element = the footprint of one fp32 tensor
     if (ws_get(h, "h16", (size_t)B * T * R, &t1) || ws_get(h, "o16", (size_t)B * T * G, &t2) ||
         ws_get(h, "c16", (size_t)B * T * CI, &t3)) return 1;
     h16 = (__half*)t1; o16 = (__half*)t2; c16 = (__half*)t3;
     if (make_tmap_hl16(&tm_h, h16, B, T, R) || make_tmap_hl16(&tm_o, o16, B, T, G) || make_tmap_hl16(&tm_c, c16, B, T, CI)) return 1;
+    if (use_fused() && make_tmap_hl16(&tm_h32, h16, B, T, R, 32)) return 1;
     lx.begin("to_hl16");
     tc::to_hl16_kernel<<<dim3((T + 31) / 32, (CI + 31) / 32, B), 256, 0, st>>>(cup, c16, B, CI, T);
     lx.check();
@@ -1204,12 +1205,13 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
     const int nb = c.flow_blocks[f];
     for (int i = 0; i < nb; ++i) {
       const int d = dilation_of(c, i);
-      if (use_tc && use_fused() && K * (R / tc::BK) + (CI + tc::BK - 1) / tc::BK == fl.tc_gate[i].nchunks_total && G == 256) {
+      if (use_tc && use_fused() && K * (R / tc::BK) + (CI + tc::BK - 1) / tc::BK == fl.tc_gate[i].nchunks_total && G == 256 && T % 4 == 0) {
         // whole residual block in one kernel: o stays on chip (tc_block.cuh)
         lx.begin("block_fused");
         tc::BlockParams bp;
         memset(&bp, 0, sizeof(bp));
         bp.tmH = tm_h; bp.tmC = tm_c;
+        bp.tmHin32 = tm_h32; bp.tmHout32 = tm_hb32;
         bp.h_in16 = h16; bp.h_out16 = h16b;
         bp.W1 = fl.tc_gate[i].Wimg; bp.inv1 = fl.tc_gate[i].inv_scale; bp.bias1 = fl.tc_gate[i].bias;
         bp.W2 = fl.tc_resskip[i].Wimg; bp.inv2 = fl.tc_resskip[i].inv_scale; bp.bias2 = fl.tc_resskip[i].bias;
@@ -1237,6 +1239,7 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
         lx.end();
         std::swap(h16, h16b);          // the block's output is the next block's input
         std::swap(tm_h, tm_hb);
+        std::swap(tm_h32, tm_hb32);
         continue;
       }
       if (use_tc) {

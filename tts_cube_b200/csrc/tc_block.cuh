@@ -27,7 +27,8 @@ constexpr int BLK_SMEM = BLK_STAGES * BLK_STAGE_BYTES + BLK_O_BYTES + 1024 + 256
 static_assert(BK == 32, "tc_block_kernel is written for 32-channel K chunks (SWIZZLE_64B)");
 
 struct BlockParams {
-  CUtensorMap tmH, tmC;          // h16 [2B][T][128], c16 [2B][T][80]
+  CUtensorMap tmH, tmC;          // h16 [2B][T][128], c16 [2B][T][80]            (boxes of 32 ch x 128 rows)
+  CUtensorMap tmHin32, tmHout32; // block input / output residual stream, boxes of 32 ch x 32 rows (one epilogue warp)
   const __half* W1;              // gate images   [2 n-tiles][nch1][2][256*32]
   const __half* W2;              // res/skip images [1][8][2][256*32]
   const float* inv1; const float* bias1;   // [512]  (n-tile major: [nt*256 + col])
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
   uint64_t* o_full = acc_free + 2;             // [1] o half is in smem                          (epilogue -> MMA, 16 warps)
   uint64_t* o_free = o_full + 1;               // [1] GEMM2 has read the o half                  (MMA -> epilogue)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+  uint64_t* hbar = o_free + 2;                 // [16] per epilogue warp: its residual rows have landed in shared memory
   float2* sb1 = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [512] gate: folded exp2 factors
   float2* sb2 = sb1 + 512;                                                           // [256] res/skip
 
@@ -87,6 +89,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
     for (int r = 0; r < 2; ++r) { mbar_init(&acc_full[r], 1); mbar_init(&acc_free[r], NUM_EPI_WARPS); }
     mbar_init(o_full, NUM_EPI_WARPS);
     mbar_init(o_free, 1);
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(&hbar[w], 1);
+    prefetch_tmap(&p.tmHin32);
+    prefetch_tmap(&p.tmHout32);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -235,17 +240,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
       const int r0 = titer & 1, r1 = r0 ^ 1;
       const int len = p.lens ? min(p.lens[b], p.T) : p.T;
       const bool in_range = t < p.T, valid = t < len;
-      // pull this tile's residual rows / skip columns into L2 while the MMAs run
-      if (in_range) {
-        if (grp < 2) {
-          const __half* h0 = p.h_in16 + ((size_t)b * p.T + t) * 128 + grp * 64;
-          prefetch_l2(h0);
-          prefetch_l2(h0 + (size_t)p.B * p.T * 128);
-        } else if (!p.skip_set && (lane & 7) == 0) {
-          const float* s0 = p.skip + ((size_t)b * 128 + (grp - 2) * 64) * p.T + t;
+      // a flow's last block reads the running skip total: pull this warp's slice into L2 while the MMAs run
+      if (in_range && p.skip16 && !p.skip_set && (lane & 7) == 0) {
+        const float* s0 = p.skip + ((size_t)b * 128 + grp * 32) * p.T + t;
 #pragma unroll 8
-          for (int j = 0; j < 64; ++j) prefetch_l2(s0 + (size_t)j * p.T);
-        }
+        for (int j = 0; j < 32; ++j) prefetch_l2(s0 + (size_t)j * p.T);
       }
       // ---------------- gate epilogue of n-tile 0 (region r0) and n-tile 1 (region r1) ----------------
       for (int nt = 0; nt < 2; ++nt) {
@@ -288,6 +287,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
         if (STATS) st_acc[5] += clock64() - g_t0;       // gate math (TMEM load .. region handed back)
         BLK_WAIT(o_free, (ofree_ph & 1) ^ 1, 2 + nt);
         ++ofree_ph;
+        if (nt == 0) {   // the residual rows the previous tile stored from this warp's piece of the o buffer have been read
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
         // K-major SWIZZLE_64B A tile [128 rows][32 ch]: 16-byte piece c16 of row r lives at piece c16 ^ ((r>>1)&3)
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
@@ -304,88 +307,46 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
         if (lane == 0) mbar_arrive(o_full);
       }
       // ---------------- res/skip epilogue (GEMM2 result in region r0) ----------------
-      // The global reads of this tile's residual rows / skip columns do not depend on GEMM2: they are all issued
-      // BEFORE waiting for its accumulator, so their latency (several thousand cycles next to the TMA stream) hides
-      // behind GEMM2's second K half instead of sitting, four dependent batches deep, between this tile's GEMM2 and
-      // the gate epilogues of the next tile (measured with CUBE_BLOCK_STATS=1: that chain, not the MMAs, set the pace).
-      const uint32_t taddr_rs = tmem_base + r0 * BN + ((uint32_t)(q * 32) << 16) + (grp < 2 ? grp * 64 : 128 + (grp - 2) * 64);
-      long long r_t0 = 0;
-      if (grp < 2) {   // cols [0,128): residual stream h_in -> h_out; this warp: channels [64*grp, +64)
+      // Every warp owns 32 residual channels [32 grp, +32) and the 32 skip channels of the same index, for its 32 rows.
+      // Measured with CUBE_BLOCK_STATS=1, the read-modify-write of these two streams (not the MMAs) paced the tile
+      // loop: per-row 16-byte global accesses cost 32 L1 wavefronts per instruction, and the next tile's gate
+      // epilogues queue behind them.  So:
+      //  * residual: the warp's [32 rows][32 ch] hi/lo boxes travel by TMA through the warp's own 2 x 2 KB pieces of
+      //    the o buffer (idle once GEMM2 has read it) - load, update in place in the swizzled layout, store;
+      //  * skip (+)= s is a fire-and-forget red.global.add.f32, one 128-byte line per warp instruction (one thread
+      //    per element and launch, so no contention, and the same single round-to-nearest fp32 add a load/add/store
+      //    would do - REDG flushes subnormals, a < 1.2e-38 difference - without a load on the critical path).
+      {
+        const uint32_t taddr_rs = tmem_base + r0 * BN + ((uint32_t)(q * 32) << 16) + grp * 32;
         const size_t plane = (size_t)p.B * p.T * 128;
-        const __half* hrow = p.h_in16 + ((size_t)b * p.T + t) * 128 + grp * 64;
-        __half* orow = p.h_out16 + ((size_t)b * p.T + t) * 128 + grp * 64;
-        uint4 hreg[16];            // [ci][hi piece 0, hi piece 1, lo piece 0, lo piece 1]
+        float* sp0 = p.skip + ((size_t)b * 128 + grp * 32) * p.T + t;
+        const bool last_block = p.skip16 != nullptr;
+        const int ew = warp - 2;
+        uint8_t* piece_hi = o_smem + grp * 2 * A_TILE_BYTES + q * 2048;      // rows [32 q, +32) of K chunk grp
+        uint8_t* piece_lo = piece_hi + A_TILE_BYTES;
+        const int tw = tt * BM + q * 32;                                     // first time step of this warp's rows
+        float old[32];             // only a flow's last block needs the running skip total (relu -> fp16 planes)
+        if (last_block) {
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          if (in_range) {
-            hreg[ci * 4 + 0] = reinterpret_cast<const uint4*>(hrow + ci * 16)[0];
-            hreg[ci * 4 + 1] = reinterpret_cast<const uint4*>(hrow + ci * 16)[1];
-            hreg[ci * 4 + 2] = reinterpret_cast<const uint4*>(hrow + plane + ci * 16)[0];
-            hreg[ci * 4 + 3] = reinterpret_cast<const uint4*>(hrow + plane + ci * 16)[1];
-          } else {
-            hreg[ci * 4 + 0] = hreg[ci * 4 + 1] = hreg[ci * 4 + 2] = hreg[ci * 4 + 3] = make_uint4(0, 0, 0, 0);
-          }
+          for (int j = 0; j < 32; ++j) old[j] = (in_range && !p.skip_set) ? __ldcs(sp0 + (size_t)j * p.T) : 0.f;
         }
         BLK_WAIT(&acc_full[r0], full_ph[r0] & 1, 4);
-        if (STATS) r_t0 = clock64();
+        ++full_ph[r0];
+        const long long r_t0 = STATS ? clock64() : 0;
         tc_fence_after();
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          const int cc = grp * 64 + ci * 16;
-          uint32_t racc[16];
-          tmem_ld16(taddr_rs + ci * 16, racc);
-          tmem_ld_wait();
-          if (ci == 3) {           // last TMEM read of this warp: hand the region back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_free[r0]);
-          }
-          const uint32_t* hp = reinterpret_cast<const uint32_t*>(&hreg[ci * 4]);
-          const uint32_t* lp = reinterpret_cast<const uint32_t*>(&hreg[ci * 4 + 2]);
-          uint32_t hi2[8], lo2[8];
-#pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const float2 s0 = sb2[cc + j], s1 = sb2[cc + j + 1];
-            const float2 oh = unpack_h2(hp[j >> 1]), ol = unpack_h2(lp[j >> 1]);
-            const float v0 = fmaf(__uint_as_float(racc[j]), s0.x, s0.y), v1 = fmaf(__uint_as_float(racc[j + 1]), s1.x, s1.y);
-            const float n0 = valid ? ((oh.x + ol.x) + v0) * p.scale : 0.f;
-            const float n1 = valid ? ((oh.y + ol.y) + v1) * p.scale : 0.f;
-            split16x2(n0, n1, hi2[j >> 1], lo2[j >> 1]);
-          }
-          if (in_range) {
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-              reinterpret_cast<uint4*>(orow + ci * 16)[v] = make_uint4(hi2[4 * v], hi2[4 * v + 1], hi2[4 * v + 2], hi2[4 * v + 3]);
-              reinterpret_cast<uint4*>(orow + plane + ci * 16)[v] = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
-            }
-          }
+        if (lane == 0) {           // GEMM2 is complete: the o buffer is idle, fetch the residual rows into this warp's pieces
+          mbar_expect_tx(&hbar[ew], 2 * 2048);
+          tma_load_3d(piece_hi, &p.tmHin32, &hbar[ew], grp * 32, tw, b);
+          tma_load_3d(piece_lo, &p.tmHin32, &hbar[ew], grp * 32, tw, p.B + b);
         }
-      } else {         // cols [128,256): skip accumulator fp32 [B][128][T] (lanes = consecutive t: one 128-B line per
-                       // column and warp - measured faster than a channels-last row per thread); channels [64*(grp-2), +64)
-        float* sp0 = p.skip + ((size_t)b * 128 + (grp - 2) * 64) * p.T + t;
-        float old[64];
-        if (in_range && !p.skip_set) {
+        // ---- skip columns [128 + 32 grp, +32) ----
 #pragma unroll
-          for (int j = 0; j < 64; ++j) old[j] = __ldcs(sp0 + (size_t)j * p.T);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 64; ++j) old[j] = 0.f;
-        }
-        BLK_WAIT(&acc_full[r0], full_ph[r0] & 1, 4);
-        if (STATS) r_t0 = clock64();
-        tc_fence_after();
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          const int cc = (grp - 2) * 64 + ci * 16;
+        for (int ci = 0; ci < 2; ++ci) {
+          const int cc = grp * 32 + ci * 16;
           uint32_t racc[16];
-          tmem_ld16(taddr_rs + ci * 16, racc);
+          tmem_ld16(taddr_rs + 128 + ci * 16, racc);
           tmem_ld_wait();
-          if (ci == 3) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_free[r0]);
-          }
-          if (p.skip16) {
+          if (last_block) {
             uint32_t hi2[8], lo2[8];
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
@@ -396,26 +357,72 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
             }
             if (in_range) {
               __half* srow = p.skip16 + ((size_t)b * p.T + t) * 128 + cc;
-              const size_t splane = (size_t)p.B * p.T * 128;
 #pragma unroll
               for (int v = 0; v < 2; ++v) {
                 reinterpret_cast<uint4*>(srow)[v] = make_uint4(hi2[4 * v], hi2[4 * v + 1], hi2[4 * v + 2], hi2[4 * v + 3]);
-                reinterpret_cast<uint4*>(srow + splane)[v] = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
+                reinterpret_cast<uint4*>(srow + plane)[v] = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
               }
             }
           } else if (in_range) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 s2 = sb2[128 + cc + j];
-              const float y = old[ci * 16 + j] + fmaf(__uint_as_float(racc[j]), s2.x, s2.y);
-              __stcs(sp0 + (size_t)(ci * 16 + j) * p.T, valid ? y : 0.f);
+              const float y = valid ? fmaf(__uint_as_float(racc[j]), s2.x, s2.y) : 0.f;
+              float* dst = sp0 + (size_t)(ci * 16 + j) * p.T;
+              if (p.skip_set) __stcs(dst, y);
+              else asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst), "f"(y) : "memory");
             }
           }
         }
+        // ---- residual columns [32 grp, +32): h_out = (h_in + r) * sqrt(.5), in place in the swizzled pieces ----
+        mbar_wait(&hbar[ew], titer & 1);
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int cc = grp * 32 + ci * 16;
+          uint32_t racc[16];
+          tmem_ld16(taddr_rs + ci * 16, racc);
+          // K-major SWIZZLE_64B: 16-byte piece c16 of row r lives at piece c16 ^ ((r >> 1) & 3) of its 64-byte row
+          const uint32_t off0 = lane * 64 + (((ci * 2) ^ ((lane >> 1) & 3)) << 4);
+          const uint32_t off1 = lane * 64 + (((ci * 2 + 1) ^ ((lane >> 1) & 3)) << 4);
+          uint4 hv[2], lv[2];
+          hv[0] = *reinterpret_cast<const uint4*>(piece_hi + off0);
+          hv[1] = *reinterpret_cast<const uint4*>(piece_hi + off1);
+          lv[0] = *reinterpret_cast<const uint4*>(piece_lo + off0);
+          lv[1] = *reinterpret_cast<const uint4*>(piece_lo + off1);
+          tmem_ld_wait();
+          if (ci == 1) {           // last TMEM read of this warp: hand the region back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_free[r0]);
+          }
+          const uint32_t* hp = reinterpret_cast<const uint32_t*>(hv);
+          const uint32_t* lp = reinterpret_cast<const uint32_t*>(lv);
+          uint32_t hi2[8], lo2[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float2 s0 = sb2[cc + j], s1 = sb2[cc + j + 1];
+            const float2 oh = unpack_h2(hp[j >> 1]), ol = unpack_h2(lp[j >> 1]);
+            const float v0 = fmaf(__uint_as_float(racc[j]), s0.x, s0.y), v1 = fmaf(__uint_as_float(racc[j + 1]), s1.x, s1.y);
+            const float n0 = valid ? ((oh.x + ol.x) + v0) * p.scale : 0.f;
+            const float n1 = valid ? ((oh.y + ol.y) + v1) * p.scale : 0.f;
+            split16x2(n0, n1, hi2[j >> 1], lo2[j >> 1]);
+          }
+          *reinterpret_cast<uint4*>(piece_hi + off0) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
+          *reinterpret_cast<uint4*>(piece_hi + off1) = make_uint4(hi2[4], hi2[5], hi2[6], hi2[7]);
+          *reinterpret_cast<uint4*>(piece_lo + off0) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
+          *reinterpret_cast<uint4*>(piece_lo + off1) = make_uint4(lo2[4], lo2[5], lo2[6], lo2[7]);
+        }
+        fence_proxy_async();       // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {           // rows beyond T are clipped by the tensor map
+          tma_store_3d(&p.tmHout32, piece_hi, grp * 32, tw, b);
+          tma_store_3d(&p.tmHout32, piece_lo, grp * 32, tw, p.B + b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (STATS) st_acc[6] += clock64() - r_t0;     // res/skip epilogue after the accumulator arrived
       }
-      ++full_ph[r0];
-      if (STATS) st_acc[grp < 2 ? 6 : 7] += clock64() - r_t0;   // residual / skip read-modify-write
     }
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until the bulk engine has read it
     if (STATS && p.stats && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 10)) {
       unsigned long long* o = p.stats + (warp == 2 ? 11 : 19);
       for (int i = 0; i < 8; ++i) atomicAdd(o + i, (unsigned long long)st_acc[i]);
