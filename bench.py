@@ -42,7 +42,7 @@ BLOCK_FLOPS = GATE_FLOPS + 2.0 * (256 * 256)               # + res/skip 1x1 256 
 BLOCK_BYTES = 4.0 * (128 + 80 + 128 + 128 + 128)           # read h, c_up, skip; write h', skip (fp32 equivalents)
 HIFI_FLOPS_PER_SAMPLE = 1022.2e3                           # SURVEY 8(d), neb-noft rates
 HIFI_BYTES_PER_SAMPLE = 9021.0
-FUSED_TRAFFIC = 4.16e9                                     # dram read + write of one tc_block_kernel launch (ncu)
+FUSED_TRAFFIC = 3.23e9                                     # dram read + write of one tc_block_kernel launch (ncu --set full)
 PWN_FLOPS_PER_SAMPLE = 25.63e6
 PWN_BYTES_PER_SAMPLE = 103609.0
 
