@@ -166,6 +166,40 @@ int cube_categorical_sample(const float* logits, const float* u, int64_t* idx, i
 /* cube/api.py:65: int16(audio * 32767), truncation toward zero */
 int cube_wav_to_int16(const float* wav, int16_t* out, int64_t n, cube_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Log-mel spectrogram on the device: the feature front-end of the "gold mel" callers.
+ * Replaces hifigan/meldataset.py:50-74 mel_spectrogram() (hifigan/inference.py:26, cube/networks/cubegan.py:137)
+ * and cube/io_utils/vocoder.py:54-62 MelVocoder.melspectrogram() (cube/io_utils/io_vocoder.py:56).
+ * The mel filter bank is an input (the reference gets it from librosa.filters.mel on the host).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct cube_mel cube_mel_t;
+
+typedef struct cube_mel_config {
+  int32_t n_fft;      /* 1024; multiple of 4 */
+  int32_t win_size;   /* <= n_fft (centred zero padding like torch.stft) */
+  int32_t hop_size;   /* 240 / 256; multiple of 4 */
+  int32_t n_mels;     /* 80 */
+  int32_t pad_left;   /* reflect padding: (n_fft-hop)/2 for meldataset.py:62, n_fft/2 for librosa center=True */
+  int32_t pad_right;
+  int32_t log10_out;  /* 0: ln (meldataset.py:19-20)   1: log10 (io_utils/vocoder.py:96-98) */
+  int32_t layout;     /* 0: [B, n_mels, F] (HiFi-GAN)  1: [B, F, n_mels] (MelVocoder / WaveRNN, time-major) */
+  float mag_eps;      /* sqrt(re^2 + im^2 + eps): 1e-9 in meldataset.py:70, 0 for np.abs */
+  float floor_val;    /* clamp before the log: 1e-5 */
+  float pad_value;    /* written to frames beyond an utterance's own frame count in a ragged batch */
+  float preemph;      /* 0, or 0.97 = MelVocoder._preemphasis (io_utils/vocoder.py:64-65) */
+} cube_mel_config;
+
+/* window: host [win_size] or NULL = periodic Hann (torch.hann_window / scipy 'hann', fftbins=True);
+ * mel_basis: host [n_mels][n_fft/2 + 1], row-major. */
+int cube_mel_create(cube_mel_t** out, const cube_mel_config* cfg, const float* window, const float* mel_basis, int device);
+/* frames of an utterance of n_samples samples (0 when reflect padding is impossible: n_samples <= pad) */
+int64_t cube_mel_out_frames(const cube_mel_t* h, int64_t n_samples);
+/* wav: device [B, Tmax]; n_samples: HOST [B] or NULL (= Tmax each); mel: device, Fmax frames per utterance
+ * (Fmax >= cube_mel_out_frames(max n_samples)); rows beyond an utterance's frame count hold pad_value. */
+int cube_mel_forward(cube_mel_t* h, const float* wav, const int32_t* n_samples, float* mel, int B, int64_t Tmax,
+                     int64_t Fmax, cube_stream_t stream);
+void cube_mel_destroy(cube_mel_t* h);
+
 #ifdef __cplusplus
 }
 #endif

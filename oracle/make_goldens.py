@@ -12,6 +12,7 @@ imported from where they lie and only their numerical outputs are stored.
                        (weights NOT stored - staged by oracle/stage_weights.py), F=24
   heads.npz            cube/networks/loss.py MULAW/RAW/MOL/Gaussian encode/decode/sample
   upsample2.npz        cube/networks/modules.py UpsampleNet2/R/I (+ teacher upsample weights)
+  mel_hifigan.npz      hifigan/meldataset.py:mel_spectrogram (librosa stubbed with torchaudio's Slaney filter bank)
   clarinet_regress.npz NOT reference-derived (no forward code in the reference): regression
                        snapshot of oracle/clarinet_ref.py with the shipped checkpoints
 """
@@ -147,7 +148,9 @@ def main():
     print("clarinet_regress", tuple(xs.shape), "std", float(xs.std()), "peak", float(xs.abs().max()))
 
 
-if __name__ == "__main__" and "--inc-only" not in sys.argv:
+_ONLY = {"--inc-only", "--wavernn", "--mel"} & set(sys.argv)      # no flag: regenerate everything
+
+if __name__ == "__main__" and not _ONLY:
     main()
 
 
@@ -166,7 +169,7 @@ def write_mulaw_inc():
         f.write("\n};\n")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and (not _ONLY or "--inc-only" in _ONLY):
     write_mulaw_inc()
 
 
@@ -205,5 +208,51 @@ def wavernn_goldens():
         print("wavernn", out, np.asarray(y).shape, float(np.abs(y).max()))
 
 
-if __name__ == "__main__" and ("--wavernn" in sys.argv or "--inc-only" not in sys.argv):
+if __name__ == "__main__" and (not _ONLY or "--wavernn" in _ONLY):
     wavernn_goldens()
+
+
+def mel_goldens():
+    """tests/golden/mel_hifigan.npz: the UNMODIFIED hifigan/meldataset.py:mel_spectrogram executed here.
+    Harness shims (the reference files are untouched): `librosa` is not installed, so a stub module provides
+    `filters.mel` from torchaudio's Slaney filter bank (an implementation independent of ours) and inert
+    `load` / `util.normalize`; torch.stft gets `return_complex=False` (mandatory since torch 2.0, absent in the
+    torch==1.4 reference call)."""
+    import torchaudio
+    from oracle import mel_ref as M
+
+    def mel_fn(sr, n_fft, n_mels, fmin, fmax):
+        return torchaudio.functional.melscale_fbanks(n_fft // 2 + 1, float(fmin), float(fmax), n_mels, sr, norm="slaney",
+                                                     mel_scale="slaney").T.contiguous().numpy()
+
+    lib = types.ModuleType("librosa")
+    lib.load = lambda *a, **k: None
+    lib.util = types.ModuleType("librosa.util")
+    lib.util.normalize = lambda x, *a, **k: x
+    lib.filters = types.ModuleType("librosa.filters")
+    lib.filters.mel = mel_fn
+    for k, v in (("librosa", lib), ("librosa.util", lib.util), ("librosa.filters", lib.filters)):
+        sys.modules[k] = v
+    sys.path.insert(0, os.path.join(REF, "hifigan"))
+    import meldataset as ref_md  # noqa (reference hifigan/meldataset.py)
+
+    real_stft = torch.stft
+    torch.stft = lambda *a, **k: real_stft(*a, **{"return_complex": False, **k})
+    try:
+        out = {}
+        # (a) the shipped vocoder's front-end (neb-noft config: 22 050 Hz, hop 256... values from its config.json),
+        # (b) the call Cubegan makes (cube/networks/cubegan.py:137: 1024, 80, 24000, 240, 1024, 0, 12000)
+        for tag, args in (("a", (1024, 80, 22050, 256, 1024, 0, 8000)), ("b", (1024, 80, 24000, 240, 1024, 0, 12000))):
+            ref_md.mel_basis.clear(); ref_md.hann_window.clear()
+            y = M.test_signal(2, 47 * args[3], seed=5 if tag == "a" else 6, sr=args[2])
+            mel = ref_md.mel_spectrogram(y, *args)
+            out[f"y_{tag}"] = y.numpy(); out[f"mel_{tag}"] = mel.numpy(); out[f"args_{tag}"] = np.asarray(args)
+            out[f"basis_{tag}"] = mel_fn(args[2], args[0], args[1], args[5], args[6])
+            print("mel", tag, tuple(mel.shape), float(mel.min()), float(mel.max()))
+        np.savez_compressed(os.path.join(OUT, "mel_hifigan.npz"), **out)
+    finally:
+        torch.stft = real_stft
+
+
+if __name__ == "__main__" and (not _ONLY or "--mel" in _ONLY):
+    mel_goldens()

@@ -414,3 +414,90 @@ def test_hifigan_tcgen05_edge_cases(dev):
             assert float((y - ref).abs().max()) <= TOL, (F_, frames)
             if frames:
                 assert float(y[0].abs().max()) == 0.0
+
+
+# ------------------------------------------------ mel front-end ------------------------------------------------
+MEL_TOL = 2e-4      # log-mel units (fp32 DFT by direct summation vs torch's FFT; measured ~1e-5)
+
+
+def test_mel_hifigan_golden_and_oracle(dev):
+    import tts_cube_b200 as cube
+    from oracle import mel_ref as M
+    d = load_golden("mel_hifigan.npz")
+    for tag in "ab":
+        a = [int(v) for v in d[f"args_{tag}"]]
+        y = torch.from_numpy(d[f"y_{tag}"])
+        mel = cube.mel_spectrogram(y.to(dev), *a).cpu().numpy()
+        err = float(np.abs(mel - d[f"mel_{tag}"]).max())
+        print(f"mel golden {tag}: max-abs {err:.2e}")
+        assert mel.shape == d[f"mel_{tag}"].shape and err <= MEL_TOL
+    # longer, ragged batch with a silent stretch (hits the 1e-5 clamp) against the oracle
+    n_fft, M_, sr, hop, win, fmin, fmax = 1024, 80, 22050, 256, 1024, 0, 8000
+    y = M.test_signal(3, 40000, seed=9)
+    y[1, 12000:20000] = 0.0
+    lens = [40000, 30000 - 37, 2049]
+    fe = cube.MelSpectrogram(n_fft, M_, sr, hop, win, fmin, fmax)
+    out = fe(y.to(dev), n_samples=lens).cpu()
+    assert out.shape == (3, 80, fe.n_frames(40000))
+    for b, L in enumerate(lens):
+        ref = M.hifigan_mel_spectrogram(y[b:b + 1, :L], n_fft, M_, sr, hop, win, fmin, fmax)[0]
+        F = ref.shape[1]
+        assert F == fe.n_frames(L)
+        assert float((out[b, :, :F] - ref).abs().max()) <= MEL_TOL
+        assert bool((out[b, :, F:] == float(np.log(1e-5))).all())
+    assert float(out[1].min()) == pytest.approx(float(np.log(1e-5)), abs=1e-6)      # the silent stretch sits on the floor
+
+
+def test_mel_cube_flavour(dev):
+    import tts_cube_b200 as cube
+    from oracle import mel_ref as M
+    y = M.test_signal(1, 30000, seed=4)[0]
+    for pre in (False, True):
+        ref = M.cube_melspectrogram(y, 22050, 80, 256, use_preemphasis=pre).numpy()
+        got = cube.MelVocoder().melspectrogram(y.numpy(), 22050, 80, 256, use_preemphasis=pre, device=dev)
+        assert got.shape == ref.shape and got.dtype == np.float32
+        assert float(np.abs(got - ref).max()) <= MEL_TOL
+    # 24 kHz / hop 240 (the Cubegan call), too-short input -> error from the library, not garbage
+    fe = cube.MelSpectrogram(1024, 80, 24000, 240, 1024, 0, 12000)
+    assert fe(torch.zeros(1, 300, device=dev)).shape == (1, 80, 1)       # shorter than the padding: zero frames, one padded row
+    with pytest.raises(cube.CubeVocError):
+        cube.MelSpectrogram(1024, 80, 24000, 250, 1024, 0, 12000)(torch.zeros(1, 4000, device=dev))   # hop not a multiple of 4
+
+
+def test_mel_copy_synthesis_chain(dev, neb):
+    """wav -> device mel -> HiFi-GAN (the hifigan/inference.py:26-45 copy-synthesis chain) stays on the GPU and matches
+    the same chain through the CPU oracles."""
+    import tts_cube_b200 as cube
+    from oracle import mel_ref as M
+    sd, cfg = neb
+    y = M.test_signal(1, 16 * 256, seed=12)
+    args = (1024, 80, 22050, 256, 1024, 0, 8000)
+    mel = cube.mel_spectrogram(y.to(dev), *args)
+    g = _gen(cfg, sd, dev, 1)
+    with torch.no_grad():
+        wav = g(mel).cpu()
+    ref = H.generator_forward(sd, cfg, M.hifigan_mel_spectrogram(y, *args))
+    assert wav.shape == ref.shape
+    assert float((wav - ref).abs().max()) <= TOL
+
+
+# ------------------------------------------------ kernel variants behind env switches ------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("env,select", [
+    pytest.param({"CUBE_TC_FUSED": "0"}, "student and tcgen05", id="student_unfused_pair"),
+    pytest.param({"CUBE_TC_FUSED": "0", "CUBE_TC_CG2": "1"}, "student and tcgen05 and not full_length", id="student_cta_pair"),
+    pytest.param({"CUBE_TC_WIN": "0"}, "hifigan and tcgen05 and not full_size and not loudness", id="hifigan_no_window"),
+])
+def test_variants_in_subprocess(env, select):
+    """The library reads its kernel-selection switches once per process, so the non-default variants (gate + res/skip
+    pair instead of the fused block kernel, CTA-pair MMA, per-tap staging instead of window mode) are exercised by
+    re-running the matching parity tests in a child process with the switch set."""
+    import os
+    import subprocess
+    import sys
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        f"({select}) and not subprocess"], env=e, capture_output=True, text=True, timeout=600)
+    tail = (r.stdout or "")[-1500:] + (r.stderr or "")[-500:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout, tail

@@ -7,6 +7,7 @@ import subprocess
 import sys
 import textwrap
 
+import numpy as np
 import pytest
 import torch
 
@@ -30,6 +31,27 @@ def test_config_struct_matches_header_size():
     from tts_cube_b200 import _lib
     # 3 + 2 + 8 + 8 + 2 + 8 + 8 + 64 + 1 + 8 + 3 + 2 + 2 + 1 + 4 int32 fields
     assert ctypes.sizeof(_lib.VocConfig) == 4 * (3 + 2 + 16 + 2 + 16 + 64 + 1 + 8 + 3 + 2 + 2 + 1 + 4 + 6)
+    assert ctypes.sizeof(_lib.MelConfig) == 4 * 12      # cube_mel_config: 8 int32 + 4 float
+
+
+def test_mel_front_end_host_logic():
+    """filter bank = the torchaudio/librosa Slaney bank stored with the reference-made golden; frame-count law;
+    without a GPU the front-end refuses to run (no CPU path)."""
+    import tts_cube_b200 as cube
+    from conftest import load_golden
+    d = load_golden("mel_hifigan.npz")
+    for tag in "ab":
+        n_fft, n_mels, sr, hop, win, fmin, fmax = [int(v) for v in d[f"args_{tag}"]]
+        b = cube.slaney_mel_basis(sr, n_fft, n_mels, fmin, fmax)
+        assert b.shape == (n_mels, n_fft // 2 + 1) and b.dtype == np.float32
+        assert float(np.abs(b - d[f"basis_{tag}"]).max()) <= 1e-6 * float(b.max()) * 10
+        m = cube.MelSpectrogram(n_fft, n_mels, sr, hop, win, fmin, fmax)
+        assert m.n_frames(47 * hop) == 47 and m.n_frames(47 * hop + hop - 1) == 47 and m.n_frames((n_fft - hop) // 2) == 0
+    c = cube.MelSpectrogram(flavor="cube", hop_size=256)
+    assert c.n_frames(1000) == 1 + 1000 // 256 and c.cfg.layout == 1 and c.cfg.log10_out == 1
+    if not torch.cuda.is_available():
+        with pytest.raises(cube.CubeVocError):
+            cube.mel_spectrogram(torch.zeros(1, 4096), 1024, 80, 22050, 256, 1024, 0, 8000)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")

@@ -136,3 +136,33 @@ def test_wavernn_fold_unfold():
     assert float(x[0, :10].abs().max()) == 0.0 and torch.equal(x[1, :10], xl[0, 11:21])
     y = torch.arange(20 * 300, dtype=torch.float).reshape(20, 300)
     assert R.unfold_batch(y, 100).shape == (1, 20 * 200)
+
+
+def test_mel_oracle_matches_reference():
+    """oracle/mel_ref.py vs the unmodified hifigan/meldataset.py:mel_spectrogram run in the build container
+    (tests/golden/mel_hifigan.npz), with the oracle's OWN Slaney filter bank against the torchaudio one the golden used."""
+    from oracle import mel_ref as M
+    d = load_golden("mel_hifigan.npz")
+    for tag in "ab":
+        a = [int(v) for v in d[f"args_{tag}"]]
+        basis = M.slaney_mel_basis(a[2], a[0], a[1], a[5], a[6])
+        assert float(np.abs(basis - d[f"basis_{tag}"]).max()) <= 2e-7
+        # every filter has unit area in Hz (Slaney normalisation) up to the sampling of the triangle on the FFT grid
+        area = basis.sum(1) * (a[2] / a[0])
+        assert float(np.abs(area[5:-1] - 1.0).max()) < 0.1
+        mel = M.hifigan_mel_spectrogram(torch.from_numpy(d[f"y_{tag}"]), *a).numpy()
+        assert mel.shape == d[f"mel_{tag}"].shape
+        assert float(np.abs(mel - d[f"mel_{tag}"]).max()) <= 5e-5
+
+
+def test_mel_cube_flavour_properties():
+    """MelVocoder restatement: frame law of librosa center=True, log10 floor -5 on silence, pre-emphasis = lfilter([1,-.97])."""
+    from oracle import mel_ref as M
+    y = M.test_signal(1, 5000, seed=3)[0]
+    m = M.cube_melspectrogram(y, 22050, 80, 256)
+    assert tuple(m.shape) == (1 + 5000 // 256, 80)
+    z = M.cube_melspectrogram(torch.zeros(3000), 22050, 80, 256)
+    assert float(z.max()) == -5.0 and float(z.min()) == -5.0
+    yp = y.clone()
+    yp[1:] = y[1:] - 0.97 * y[:-1]
+    assert torch.allclose(M.cube_melspectrogram(y, 22050, 80, 256, use_preemphasis=True), M.cube_melspectrogram(yp, 22050, 80, 256))

@@ -5,6 +5,7 @@ Host side mirrors the reference's interfaces for this path:
   ``ParallelWaveNetVocoder``   ClariNet IAF student + UpsampleNet2 (weights shipped by the reference)
   ``WaveRNNVocoder`` / ``CubenetVocoder``  autoregressive WaveRNN path (cube/networks/modules.py:392-503, vocoder.py)
   ``MULAWOutput`` ...          output heads of ``cube/networks/loss.py``
+  ``mel_spectrogram`` / ``MelVocoder``  log-mel front-ends (hifigan/meldataset.py:50-74, cube/io_utils/vocoder.py:54-62)
   ``synthesize``               batch entry (mel list -> audio), sharded over ranks under torchrun
 All compute happens in libcube_vocoder.so (C ABI in include/cube_vocoder.h).
 """
@@ -14,5 +15,6 @@ from .clarinet import ParallelWaveNetVocoder  # noqa: F401
 from .heads import MULAWOutput, RAWOutput, MOLOutput, GaussianOutput  # noqa: F401
 from .wavernn import WaveRNNVocoder, CubenetVocoder  # noqa: F401
 from .api import synthesize, lpt_shard  # noqa: F401
+from .mel import MelSpectrogram, MelVocoder, mel_spectrogram, slaney_mel_basis  # noqa: F401
 
 __version__ = "0.1.0"

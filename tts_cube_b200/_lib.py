@@ -36,6 +36,12 @@ class VocConfig(C.Structure):
     ]
 
 
+class MelConfig(C.Structure):
+    _fields_ = [("n_fft", C.c_int32), ("win_size", C.c_int32), ("hop_size", C.c_int32), ("n_mels", C.c_int32),
+                ("pad_left", C.c_int32), ("pad_right", C.c_int32), ("log10_out", C.c_int32), ("layout", C.c_int32),
+                ("mag_eps", C.c_float), ("floor_val", C.c_float), ("pad_value", C.c_float), ("preemph", C.c_float)]
+
+
 class CubeVocError(RuntimeError):
     pass
 
@@ -70,6 +76,10 @@ SYMBOLS = {
     "cube_gaussian_sample": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "cube_categorical_sample": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P]),
     "cube_wav_to_int16": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "cube_mel_create": (C.c_int, [C.POINTER(_P), C.POINTER(MelConfig), _P, _P, C.c_int]),
+    "cube_mel_out_frames": (C.c_int64, [_P, C.c_int64]),
+    "cube_mel_forward": (C.c_int, [_P, _P, C.POINTER(C.c_int32), _P, C.c_int, C.c_int64, C.c_int64, _P]),
+    "cube_mel_destroy": (None, [_P]),
 }
 
 

@@ -19,6 +19,7 @@
 #include "tc_conv.cuh"
 #include "tc_block.cuh"
 #include "wavernn.cuh"
+#include "melspec.cuh"
 
 #define CUBE_VERSION "0.1.0"
 #ifndef CUBE_FUSED_DEFAULT
@@ -1810,6 +1811,120 @@ int cube_wav_to_int16(const float* wav, int16_t* out, int64_t n, cube_stream_t s
   wav_to_int16_kernel<<<head_grid(n), 256, 0, (cudaStream_t)s>>>(wav, out, n);
   CU_TRY(cudaGetLastError());
   return 0;
+}
+
+// ---- log-mel spectrogram ----
+struct cube_mel {
+  cube_mel_config cfg;
+  int device = 0, n_bins = 0, KB = 0;
+  float *cosT = nullptr, *sinT = nullptr, *basis = nullptr;
+  int *k_lo = nullptr, *k_hi = nullptr, *d_len = nullptr;
+  int len_cap = 0;
+  size_t smem = 0;
+};
+
+int cube_mel_create(cube_mel_t** out, const cube_mel_config* cfg, const float* window, const float* mel_basis, int device) {
+  using namespace cube;
+  if (!out || !cfg || !mel_basis) return fail("null argument");
+  const cube_mel_config& c = *cfg;
+  if (c.n_fft < 16 || c.n_fft > 4096 || c.n_fft % 4) return fail("n_fft must be a multiple of 4 in [16, 4096] (got %d)", c.n_fft);
+  if (c.hop_size < 4 || c.hop_size % 4) return fail("hop_size must be a positive multiple of 4 (got %d)", c.hop_size);
+  if (c.win_size < 1 || c.win_size > c.n_fft) return fail("win_size must be in [1, n_fft] (got %d)", c.win_size);
+  if (c.n_mels < 1 || c.n_mels > 512) return fail("n_mels out of range (%d)", c.n_mels);
+  if (c.pad_left < 0 || c.pad_right < 0) return fail("negative padding");
+  if (c.layout != 0 && c.layout != 1) return fail("layout must be 0 ([B,M,F]) or 1 ([B,F,M])");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("no CUDA device: libcube_vocoder has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
+  CU_TRY(cudaSetDevice(device));
+  cube_mel* h = new cube_mel();
+  h->cfg = c; h->device = device;
+  h->n_bins = c.n_fft / 2 + 1;
+  h->KB = (h->n_bins + mel::BT - 1) / mel::BT * mel::BT;
+  h->smem = mel::smem_bytes(c.n_fft, c.hop_size, h->KB);
+  if (h->smem > 220 * 1024) { delete h; return fail("n_fft/hop too large for one CTA's shared memory (%zu bytes)", h->smem); }
+  // window (centred in n_fft like torch.stft) folded into the DFT tables, all in double on the host
+  const double PI = 3.14159265358979323846;
+  std::vector<double> w(c.n_fft, 0.0);
+  const int wl = (c.n_fft - c.win_size) / 2;
+  for (int i = 0; i < c.win_size; ++i) w[wl + i] = window ? (double)window[i] : 0.5 - 0.5 * cos(2.0 * PI * i / c.win_size);
+  std::vector<float> ct((size_t)c.n_fft * h->KB, 0.f), st((size_t)c.n_fft * h->KB, 0.f);
+  for (int n = 0; n < c.n_fft; ++n)
+    for (int k = 0; k < h->n_bins; ++k) {
+      const long long r = ((long long)k * n) % c.n_fft;      // exact argument reduction
+      const double a = 2.0 * PI * (double)r / c.n_fft;
+      ct[(size_t)n * h->KB + k] = (float)(w[n] * cos(a));
+      st[(size_t)n * h->KB + k] = (float)(-w[n] * sin(a));
+    }
+  std::vector<int> lo(c.n_mels), hi(c.n_mels);
+  for (int m = 0; m < c.n_mels; ++m) {
+    int a = h->n_bins, b = 0;
+    for (int k = 0; k < h->n_bins; ++k)
+      if (mel_basis[(size_t)m * h->n_bins + k] != 0.f) { a = std::min(a, k); b = std::max(b, k + 1); }
+    lo[m] = std::min(a, b); hi[m] = b;
+  }
+  auto up = [&](const void* src, size_t bytes, void** dst) -> int {
+    CU_TRY(cudaMalloc(dst, bytes));
+    CU_TRY(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+  };
+  if (up(ct.data(), ct.size() * 4, (void**)&h->cosT) || up(st.data(), st.size() * 4, (void**)&h->sinT) ||
+      up(mel_basis, (size_t)c.n_mels * h->n_bins * 4, (void**)&h->basis) || up(lo.data(), lo.size() * 4, (void**)&h->k_lo) ||
+      up(hi.data(), hi.size() * 4, (void**)&h->k_hi)) {
+    cube_mel_destroy(h);
+    return 1;
+  }
+  CU_TRY(cudaFuncSetAttribute(mel::melspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  *out = h;
+  return 0;
+}
+
+int64_t cube_mel_out_frames(const cube_mel_t* h, int64_t n_samples) {
+  if (!h || n_samples < 0 || n_samples > INT32_MAX) return -1;
+  return cube::mel::n_frames_of((int)n_samples, h->cfg.n_fft, h->cfg.hop_size, h->cfg.pad_left, h->cfg.pad_right);
+}
+
+int cube_mel_forward(cube_mel_t* h, const float* wav, const int32_t* n_samples, float* out, int B, int64_t Tmax, int64_t Fmax,
+                     cube_stream_t stream) {
+  using namespace cube;
+  if (!h || !wav || !out) return fail("null argument");
+  if (B <= 0 || Tmax <= 0 || Fmax <= 0 || Tmax > INT32_MAX || Fmax > INT32_MAX) return fail("bad shape B=%d Tmax=%lld Fmax=%lld", B, (long long)Tmax, (long long)Fmax);
+  CU_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int longest = (int)Tmax;
+  if (n_samples) {
+    longest = 0;
+    for (int b = 0; b < B; ++b) {
+      if (n_samples[b] < 0 || n_samples[b] > Tmax) return fail("n_samples[%d]=%d outside [0, Tmax=%lld]", b, n_samples[b], (long long)Tmax);
+      longest = std::max(longest, (int)n_samples[b]);
+    }
+    if (h->len_cap < B) {
+      if (h->d_len) CU_TRY(cudaFree(h->d_len));
+      CU_TRY(cudaMalloc(&h->d_len, (size_t)B * sizeof(int)));
+      h->len_cap = B;
+    }
+    CU_TRY(cudaMemcpyAsync(h->d_len, n_samples, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  if (cube_mel_out_frames(h, longest) > Fmax) return fail("Fmax=%lld is smaller than the %lld frames of the longest utterance", (long long)Fmax, (long long)cube_mel_out_frames(h, longest));
+  mel::MelParams p;
+  p.wav = wav; p.n_samples = n_samples ? h->d_len : nullptr;
+  p.cosT = h->cosT; p.sinT = h->sinT; p.basis = h->basis; p.k_lo = h->k_lo; p.k_hi = h->k_hi; p.out = out;
+  p.B = B; p.Tmax = (int)Tmax; p.Fmax = (int)Fmax;
+  p.n_fft = h->cfg.n_fft; p.hop = h->cfg.hop_size; p.n_bins = h->n_bins; p.KB = h->KB; p.n_mels = h->cfg.n_mels;
+  p.pad_left = h->cfg.pad_left; p.pad_right = h->cfg.pad_right; p.layout = h->cfg.layout; p.log10_out = h->cfg.log10_out;
+  p.mag_eps = h->cfg.mag_eps; p.floor_val = h->cfg.floor_val; p.pad_value = h->cfg.pad_value; p.preemph = h->cfg.preemph;
+  dim3 grid((unsigned)((Fmax + mel::FT - 1) / mel::FT), (unsigned)B);
+  mel::melspec_kernel<<<grid, mel::THREADS, h->smem, st>>>(p);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+void cube_mel_destroy(cube_mel_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (void* q : {(void*)h->cosT, (void*)h->sinT, (void*)h->basis, (void*)h->k_lo, (void*)h->k_hi, (void*)h->d_len})
+    if (q) cudaFree(q);
+  delete h;
 }
 
 }  // extern "C"
