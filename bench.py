@@ -24,6 +24,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: NCCL's own banner / debug output (it defaults to stdout) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import torch  # noqa: E402
 
@@ -419,7 +421,7 @@ def main():
     whole["tensor_frac_whole_path"] = whole["flops_per_sample"] * value / world / 1e12 / pk["tf_sust"]
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only (the N>1 lines carry null)
         threads, _ = best_cpu_threads(arch, weights)
         rate, _, _ = cpu_oracle_rate(arch, weights, 48 if arch == "student" else 96, threads)
         hop = 256 if arch == "student" else 240
