@@ -364,6 +364,11 @@ struct Up2dP {
 };
 
 __global__ void __launch_bounds__(256) upsample2d_kernel(const Up2dP p) {
+  // the tap index depends on t mod s, i.e. differs between lanes: a per-lane index into the kernel-parameter
+  // (constant) bank is replayed once per distinct address, so the taps go through shared memory first
+  __shared__ float sw[3 * 64];
+  if (threadIdx.x < 3 * 64) sw[threadIdx.x] = p.w[threadIdx.x];
+  __syncthreads();
   const int t = blockIdx.x * 256 + threadIdx.x;
   const int f = blockIdx.y, b = blockIdx.z;
   if (t >= p.L_out) return;
@@ -378,12 +383,48 @@ __global__ void __launch_bounds__(256) upsample2d_kernel(const Up2dP p) {
     const int fi = f + 1 - kf;
     if (fi < 0 || fi >= p.nf) continue;
     const float* __restrict__ row = sb + (long long)fi * p.L_in;
-    if (s_hi < slen) a = fmaf(p.w[kf * 2 * p.s + k_hi], __ldg(row + s_hi), a);
-    if (s_hi - 1 >= 0 && s_hi - 1 < slen) a = fmaf(p.w[kf * 2 * p.s + k_hi + p.s], __ldg(row + s_hi - 1), a);
+    if (s_hi < slen) a = fmaf(sw[kf * 2 * p.s + k_hi], __ldg(row + s_hi), a);
+    if (s_hi - 1 >= 0 && s_hi - 1 < slen) a = fmaf(sw[kf * 2 * p.s + k_hi + p.s], __ldg(row + s_hi - 1), a);
   }
   a = a > 0.f ? a : a * p.slope;
   if (t >= slen * p.s) a = 0.f;
   p.out[((long long)b * p.nf + f) * p.L_out + t] = a;
+}
+
+// Same layer, four consecutive outputs per thread (s, pad and L_out multiples of 4: the four share their two source
+// columns, so 6 loads feed 24 FMAs and one 16-byte store).  Grid: (ceil(L_out/4/256), nf, B).
+__global__ void __launch_bounds__(256) upsample2d_x4_kernel(const Up2dP p) {
+  __shared__ float sw[3 * 64];
+  if (threadIdx.x < 3 * 64) sw[threadIdx.x] = p.w[threadIdx.x];
+  __syncthreads();
+  const int t = (blockIdx.x * 256 + threadIdx.x) * 4;
+  const int f = blockIdx.y, b = blockIdx.z;
+  if (t >= p.L_out) return;
+  const int slen = p.src_lens ? min(p.src_lens[b] * p.lens_scale, p.L_in) : p.L_in;
+  const int tp = t + p.pad;
+  const int s_hi = tp / p.s;
+  const int k_hi = tp - s_hi * p.s;          // multiple of 4, k_hi + 3 < s
+  const float* __restrict__ sb = p.src + ((long long)b * p.nf) * p.L_in;
+  float a[4] = {p.bias, p.bias, p.bias, p.bias};
+#pragma unroll
+  for (int kf = 0; kf < 3; ++kf) {
+    const int fi = f + 1 - kf;
+    if (fi < 0 || fi >= p.nf) continue;
+    const float* __restrict__ row = sb + (long long)fi * p.L_in;
+    const float x0 = (s_hi < slen) ? __ldg(row + s_hi) : 0.f;
+    const float x1 = (s_hi - 1 >= 0 && s_hi - 1 < slen) ? __ldg(row + s_hi - 1) : 0.f;
+    const float4 w0 = *reinterpret_cast<const float4*>(sw + kf * 2 * p.s + k_hi);
+    const float4 w1 = *reinterpret_cast<const float4*>(sw + kf * 2 * p.s + k_hi + p.s);
+    a[0] = fmaf(w0.x, x0, a[0]); a[1] = fmaf(w0.y, x0, a[1]); a[2] = fmaf(w0.z, x0, a[2]); a[3] = fmaf(w0.w, x0, a[3]);
+    a[0] = fmaf(w1.x, x1, a[0]); a[1] = fmaf(w1.y, x1, a[1]); a[2] = fmaf(w1.z, x1, a[2]); a[3] = fmaf(w1.w, x1, a[3]);
+  }
+  const int tend = slen * p.s;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    a[j] = a[j] > 0.f ? a[j] : a[j] * p.slope;
+    if (t + j >= tend) a[j] = 0.f;
+  }
+  *reinterpret_cast<float4*>(p.out + ((long long)b * p.nf + f) * p.L_out + t) = make_float4(a[0], a[1], a[2], a[3]);
 }
 
 }  // namespace cube

@@ -117,6 +117,8 @@ struct cube_voc {
     std::vector<PackedConv> gate, resskip;
     std::vector<TcPacked> tc_gate, tc_resskip;
     TcPacked tc_final1;
+    TcPacked tc_front;     // front conv as a [128 x front_kernel] GEMM over the taps-as-channels planes (empty: SIMT front)
+    bool has_tc_front = false;
     float* w3 = nullptr;   // final_conv.3: [2][S] weights + [2] bias (fp32), for the fused FINAL epilogue
   };
   std::vector<Flow> flows;
@@ -560,6 +562,19 @@ static int finalize_student(cube_voc* h) {
     cube_voc::Flow& fl = h->flows[f];
     const std::string fp = "iafs." + std::to_string(f) + ".";
     if (pack_conv1d(h, fp + "front_conv.0.conv", R, 1, c.front_kernel, &fl.front)) return 1;
+    if (c.math == CUBE_MATH_TC_SPLIT16 && R == 128 && c.front_kernel % tc::BK == 0) {
+      // Conv1d(1 -> R, k, causal) == 1x1 conv over k "channels" holding the k causal taps (tc::taps_to_hl16_kernel):
+      // weight [R][1][k] read as [R][k]
+      HostTensor wf0; const HostTensor* bf0;
+      if (get_weight(h, fp + "front_conv.0.conv", &wf0) || expect_shape(fp + "front_conv.0.conv", wf0, {R, 1, c.front_kernel}) ||
+          get_bias(h, fp + "front_conv.0.conv", R, &bf0)) return 1;
+      const int nchf = c.front_kernel / tc::BK;
+      std::vector<std::vector<float>> Df(1, std::vector<float>(wf0.data.begin(), wf0.data.begin() + (size_t)R * c.front_kernel));
+      if (pack_tc_multi(h, Df, bf0->data, R, nchf, R, &fl.tc_front)) return 1;
+      fl.tc_front.nseg = 1;
+      fl.tc_front.seg[0] = {1, 1, 0, nchf, tc::BK / 16};
+      fl.has_tc_front = true;
+    }
     const int nb = c.flow_blocks[f];
     fl.gate.resize(nb); fl.resskip.resize(nb);
     for (int i = 0; i < nb; ++i) {
@@ -1138,8 +1153,13 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
       p.nf = CI; p.L_in = Lin; p.L_out = Lin * s; p.s = s; p.pad = s / 2;
       memcpy(p.w, h->up2[n].w, sizeof(p.w));
       p.bias = h->up2[n].bias; p.slope = 0.4f;
-      dim3 grid((p.L_out + 255) / 256, CI, B);
-      upsample2d_kernel<<<grid, 256, 0, st>>>(p);
+      if (s % 4 == 0 && p.pad % 4 == 0 && p.L_out % 4 == 0 && ((uintptr_t)p.out & 15) == 0) {
+        dim3 grid((p.L_out / 4 + 255) / 256, CI, B);
+        upsample2d_x4_kernel<<<grid, 256, 0, st>>>(p);
+      } else {
+        dim3 grid((p.L_out + 255) / 256, CI, B);
+        upsample2d_kernel<<<grid, 256, 0, st>>>(p);
+      }
       lx.check();
       lx.end();
       src = p.out; Lin = p.L_out; scale *= s;
@@ -1150,8 +1170,8 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
   const float* zin = noise;
   const float rs = sqrtf(0.5f);
   const bool use_tc = (c.math == CUBE_MATH_TC_SPLIT16);
-  __half *h16 = nullptr, *h16b = nullptr, *o16 = nullptr, *c16 = nullptr, *s16 = nullptr;
-  CUtensorMap tm_h, tm_hb, tm_o, tm_c, tm_s, tm_h32, tm_hb32;
+  __half *h16 = nullptr, *h16b = nullptr, *o16 = nullptr, *c16 = nullptr, *s16 = nullptr, *zc16 = nullptr;
+  CUtensorMap tm_h, tm_hb, tm_o, tm_c, tm_s, tm_h32, tm_hb32, tm_z;
   if (use_tc) {
     float *t1, *t2, *t3, *t4;
     if (ws_get(h, "s16", (size_t)B * T * S, &t4)) return 1;
@@ -1169,6 +1189,12 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
     h16 = (__half*)t1; o16 = (__half*)t2; c16 = (__half*)t3;
     if (make_tmap_hl16(&tm_h, h16, B, T, R) || make_tmap_hl16(&tm_o, o16, B, T, G) || make_tmap_hl16(&tm_c, c16, B, T, CI)) return 1;
     if (use_fused() && make_tmap_hl16(&tm_h32, h16, B, T, R, 32)) return 1;
+    if (c.front_kernel % tc::BK == 0) {   // taps-as-channels planes of z for the tensor-core front conv
+      float* t6;
+      if (ws_get(h, "zc16", (size_t)B * T * c.front_kernel, &t6)) return 1;
+      zc16 = (__half*)t6;
+      if (make_tmap_hl16(&tm_z, zc16, B, T, c.front_kernel)) return 1;
+    }
     lx.begin("to_hl16");
     tc::to_hl16_kernel<<<dim3((T + 31) / 32, (CI + 31) / 32, B), 256, 0, st>>>(cup, c16, B, CI, T);
     lx.check();
@@ -1187,7 +1213,26 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
     cube_voc::Flow& fl = h->flows[f];
     const bool last_flow = (f == c.n_flows - 1);
     float* zout = last_flow ? wav : ((f & 1) ? zb : za);
-    {  // h = relu(front_conv(z)) : causal k=32
+    if (use_tc && fl.has_tc_front) {
+      // h = relu(front_conv(z)) on the tensor cores: the k causal taps of z become k channels (fp16 planes), the conv a
+      // [T x k] x [k x 128] GEMM whose epilogue (bias, ReLU = leaky-ReLU with slope 0) writes the residual-stream planes
+      // directly - no fp32 [B][128][T] round trip and no transpose pass
+      lx.begin("front_tc");
+      tc::taps_to_hl16_kernel<<<h->sm_count * 8, 256, 0, st>>>(zin, zc16, B, T, c.front_kernel);
+      lx.check();
+      tc::TcParams tp;
+      memset(&tp, 0, sizeof(tp));
+      tp.tmA[0] = tm_z; tp.tmA[1] = tm_z;
+      tp.Wimg = fl.tc_front.Wimg; tp.inv_scale = fl.tc_front.inv_scale; tp.bias = fl.tc_front.bias;
+      tp.nseg = 1; tp.seg[0] = fl.tc_front.seg[0]; tp.nchunks_total = fl.tc_front.nchunks_total;
+      tp.B = B; tp.T = T; tp.n_tiles = fl.tc_front.n_tiles;
+      tp.lens = lens_T; tp.epi = tc::TC_EPI_CONV; tp.out16 = h16; tp.outC = R; tp.L_out = T;
+      tp.nphase = 1; tp.ostride = 1; tp.out_slope = 0.f; tp.res_inv_slope = 1.f; tp.acc_div = 1.f;
+      tp.a_inv_scale = 1.f; tp.plane_scale = 1.f;
+      launch_tc_t<128>(h, tp, st);
+      lx.check();
+      lx.end();
+    } else {  // h = relu(front_conv(z)) : causal k=32
       lx.begin("front");
       ConvP p = make_conv(fl.front);
       p.nseg = 1;

@@ -917,5 +917,33 @@ __global__ void __launch_bounds__(256) to_hl16_kernel(const float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Causal taps of a 1-channel signal as channels: z fp32 [B][T] -> fp16 hi/lo planes [2][B][T][K],
+// plane element (b, t, j) = z[b][t - (K-1) + j] (zero before the start).  Turns the ClariNet front conv
+// (Conv1d 1 -> 128, k = 32, causal) into a K-channel 1x1 GEMM for the tensor-core path.  A thread writes one
+// 16-byte piece (8 taps) of a row per plane: consecutive threads = consecutive pieces, fully coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) taps_to_hl16_kernel(const float* __restrict__ z, __half* __restrict__ dst, int B, int T, int K) {
+  const int ppr = K / 8;                                    // pieces per row
+  const long long total = (long long)B * T * ppr;
+  const size_t plane = (size_t)B * T * K;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int piece = (int)(i % ppr);
+    const long long row = i / ppr;                          // b * T + t
+    const int t = (int)(row % T);
+    const float* zb = z + (row - t);
+    const int t0 = t - (K - 1) + piece * 8;
+    uint32_t hi2[4], lo2[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const float a = (t0 + j >= 0) ? __ldg(zb + t0 + j) : 0.f;
+      const float b = (t0 + j + 1 >= 0) ? __ldg(zb + t0 + j + 1) : 0.f;
+      split16x2(a, b, hi2[j >> 1], lo2[j >> 1]);
+    }
+    reinterpret_cast<uint4*>(dst)[i] = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
+    reinterpret_cast<uint4*>(dst + plane)[i] = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
+  }
+}
+
 }  // namespace tc
 }  // namespace cube
