@@ -1919,7 +1919,6 @@ int cube_mel_create(cube_mel_t** out, const cube_mel_config* cfg, const float* w
     cube_mel_destroy(h);
     return 1;
   }
-  CU_TRY(cudaFuncSetAttribute(mel::melspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   *out = h;
   return 0;
 }
@@ -1958,6 +1957,13 @@ int cube_mel_forward(cube_mel_t* h, const float* wav, const int32_t* n_samples, 
   p.n_fft = h->cfg.n_fft; p.hop = h->cfg.hop_size; p.n_bins = h->n_bins; p.KB = h->KB; p.n_mels = h->cfg.n_mels;
   p.pad_left = h->cfg.pad_left; p.pad_right = h->cfg.pad_right; p.layout = h->cfg.layout; p.log10_out = h->cfg.log10_out;
   p.mag_eps = h->cfg.mag_eps; p.floor_val = h->cfg.floor_val; p.pad_value = h->cfg.pad_value; p.preemph = h->cfg.preemph;
+  {  // the opt-in shared-memory limit is per kernel and device, not per handle: only ever raise it
+    static size_t granted[64] = {0};
+    if (h->smem > granted[h->device & 63]) {
+      CU_TRY(cudaFuncSetAttribute(mel::melspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+      granted[h->device & 63] = h->smem;
+    }
+  }
   dim3 grid((unsigned)((Fmax + mel::FT - 1) / mel::FT), (unsigned)B);
   mel::melspec_kernel<<<grid, mel::THREADS, h->smem, st>>>(p);
   CU_TRY(cudaGetLastError());
