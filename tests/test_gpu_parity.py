@@ -11,6 +11,9 @@ from oracle import clarinet_ref as C, heads_ref as W, hifigan_ref as H
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
 MATHS = [pytest.param(0, id="fp32_simt"), pytest.param(1, id="tcgen05_split16")]
+# CUBE_TC_FP8=1 (8-bit correction passes in the student's block kernel): still inside the 1e-3 budget, but no longer at
+# fp32 round-off - the CPU emulation (profiles/r1_split_precision_study.md) predicts 3e-5 .. 5e-5
+FP8 = __import__("os").environ.get("CUBE_TC_FP8") == "1"
 
 
 @pytest.fixture(scope="module")
@@ -201,7 +204,7 @@ def test_student_small_random_weights(dev, math):
     print(f"student small math={math}: max-abs {err:.3e} (peak {float(ref.abs().max()):.2f})")
     assert float(ref.abs().max()) > 0.05
     assert err <= TOL
-    assert err <= 5e-5   # both math modes sit near fp32 round-off
+    assert err <= (3e-4 if FP8 and math == 1 else 5e-5)   # both default math modes sit near fp32 round-off
 
 
 @pytest.mark.parametrize("math", MATHS)
@@ -272,7 +275,7 @@ def test_student_full_length_properties(dev, math):
     if math == 1:
         with torch.no_grad():
             s_ = _student(ssd, tsd, dev, 0)(mel.to(dev), z.to(dev))
-        assert float((a - s_).abs().max()) <= 1e-4
+        assert float((a - s_).abs().max()) <= (5e-4 if FP8 else 1e-4)
 
 
 # ------------------------------------------------ heads ------------------------------------------------
@@ -487,6 +490,7 @@ def test_mel_copy_synthesis_chain(dev, neb):
     pytest.param({"CUBE_TC_FUSED": "0"}, "student and tcgen05", id="student_unfused_pair"),
     pytest.param({"CUBE_TC_FUSED": "0", "CUBE_TC_CG2": "1"}, "student and tcgen05 and not full_length", id="student_cta_pair"),
     pytest.param({"CUBE_TC_WIN": "0"}, "hifigan and tcgen05 and not full_size and not loudness", id="hifigan_no_window"),
+    pytest.param({"CUBE_TC_FP8": "1"}, "student and tcgen05", id="student_fp8_corrections"),
 ])
 def test_variants_in_subprocess(env, select):
     """The library reads its kernel-selection switches once per process, so the non-default variants (gate + res/skip

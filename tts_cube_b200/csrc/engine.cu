@@ -68,6 +68,7 @@ struct ProfRec { std::string name; cudaEvent_t a, b; };
 // One dense layer in tcgen05 form (tc_conv.cuh): swizzled split-fp16 weight images.
 struct TcPacked {
   __half* Wimg = nullptr;
+  uint8_t* Wimg8 = nullptr;   // CUBE_TC_FP8 variant of the gate images (see pack_tc_q8)
   float* inv_scale = nullptr;
   float* bias = nullptr;
   int N = 0, n_tiles = 0, nchunks_total = 0, nseg = 0;
@@ -312,6 +313,51 @@ static int pack_tc_multi(cube_voc* h, const std::vector<std::vector<float>>& den
   return dev_upload(h, bias, &out->bias);
 }
 
+// CUBE_TC_FP8=1: GEMM1's two correction passes of the fused block kernel on 8-bit operands (kind::f8f6f4)
+static bool use_fp8() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CUBE_TC_FP8"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+// Gate images for the 8-bit correction passes (tc_block_kernel<.., Q8>): per (n-tile, K chunk) 32 KB =
+//   [w_hi fp16, 256 rows x 64 B, SWIZZLE_64B | e4m3(w_lo), 256 x 32 B, SWIZZLE_32B | e4m3(w_hi / 16), 256 x 32 B, SWIZZLE_32B]
+// with the same per-row power-of-two scale as pack_tc_multi (so inv_scale / bias of `out` stay valid).
+static int pack_tc_q8(cube_voc* h, const std::vector<float>& dense, int N, int nchunks, TcPacked* out) {
+  using namespace tc;
+  const int bn = BN, Kp = nchunks * BK;
+  if (N % bn || BK != 32) return fail("8-bit gate images need N %% 256 == 0 and 32-channel chunks");
+  const size_t chunk_bytes = (size_t)2 * bn * BK * 2;     // 32 KB
+  std::vector<uint8_t> img((size_t)(N / bn) * nchunks * chunk_bytes, 0);
+  for (int n = 0; n < N; ++n) {
+    float mx = 0.f;
+    for (int k = 0; k < Kp; ++k) mx = std::max(mx, fabsf(dense[(size_t)n * Kp + k]));
+    int e = 0;
+    if (mx > 0.f) { int ex; frexpf(mx, &ex); e = 12 - ex; }
+    const float sc = ldexpf(1.f, e);
+    const int nt = n / bn, r = n % bn;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      uint8_t* base = img.data() + ((size_t)nt * nchunks + ch) * chunk_bytes;
+      __half* hi16 = reinterpret_cast<__half*>(base);
+      uint8_t* lo8 = base + (size_t)bn * BK * 2;
+      uint8_t* hi8 = lo8 + (size_t)bn * BK;
+      for (int kk = 0; kk < BK; ++kk) {
+        const float w = dense[(size_t)n * Kp + ch * BK + kk] * sc;
+        const __half hi = __float2half_rn(w);
+        const float hif = __half2float(hi);
+        const float lof = __half2float(__float2half_rn(w - hif));
+        hi16[swz_off(r, kk)] = hi;
+        lo8[swz32_off(r, kk)] = (uint8_t)__nv_cvt_float_to_fp8(lof, __NV_SATFINITE, __NV_E4M3);
+        hi8[swz32_off(r, kk)] = (uint8_t)__nv_cvt_float_to_fp8(hif * 0.0625f, __NV_SATFINITE, __NV_E4M3);
+      }
+    }
+  }
+  void* d;
+  if (dev_upload_bytes(h, img.data(), img.size(), &d)) return 1;
+  out->Wimg8 = (uint8_t*)d;
+  return 0;
+}
+
 static int pack_tc(cube_voc* h, const std::vector<float>& dense, const std::vector<float>& bias, int N, int nchunks,
                    TcPacked* out) {
   std::vector<std::vector<float>> d1(1, dense);
@@ -342,6 +388,25 @@ static int make_tmap_hl16(CUtensorMap* tm, const __half* base, int B, int T, int
                   tc::BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for [2*%d][%d][%d]", (int)r, B, T, C);
+  return 0;
+}
+
+// uint8 planes [2][B][T][C] channels-last -> 3-D tensor map (C, T, 2B), box (32 bytes, 128 rows, 1), 32B swizzle
+static int make_tmap_q8(CUtensorMap* tm, const uint8_t* base, int B, int T, int C) {
+  CUtensorMap probe;
+  if (make_tmap_hl16(&probe, (const __half*)base, B, T, 16)) return 1;     // resolves the driver entry point once
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+  PFN_tmapEncodeTiled fn = (PFN_tmapEncodeTiled)p;
+  if (C % 16) return fail("8-bit channels-last tensor needs C %% 16 == 0 (got %d)", C);
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)(2 * B)};
+  cuuint64_t strides[2] = {(cuuint64_t)C, (cuuint64_t)T * C};
+  cuuint32_t box[3] = {32, (cuuint32_t)tc::BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (uint8) failed (%d) for [2*%d][%d][%d]", (int)r, B, T, C);
   return 0;
 }
 
@@ -646,6 +711,7 @@ static int finalize_student(cube_voc* h) {
         tg.nseg = 2;
         tg.seg[0] = {K, 0, 0, hch, BK / 16};
         tg.seg[1] = {1, 1, 0, cch, ((CI - (cch - 1) * BK) + 15) / 16};
+        if (use_fp8() && N == 2 * BN && pack_tc_q8(h, D, N, nch, &tg)) return 1;
         // ---- res/skip: N = 256 = [128 res | 128 skip], K = G
         const int och = G / BK;
         std::vector<float> D2((size_t)(R + S) * G, 0.f), Bb2(R + S, 0.f);
@@ -1171,7 +1237,9 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
   const float rs = sqrtf(0.5f);
   const bool use_tc = (c.math == CUBE_MATH_TC_SPLIT16);
   __half *h16 = nullptr, *h16b = nullptr, *o16 = nullptr, *c16 = nullptr, *s16 = nullptr, *zc16 = nullptr;
-  CUtensorMap tm_h, tm_hb, tm_o, tm_c, tm_s, tm_h32, tm_hb32, tm_z;
+  uint8_t *h8 = nullptr, *h8b = nullptr, *c8 = nullptr;     // CUBE_TC_FP8: 8-bit planes of h (ping-pong) and c
+  CUtensorMap tm_h, tm_hb, tm_o, tm_c, tm_s, tm_h32, tm_hb32, tm_z, tm_h8, tm_h8b, tm_c8;
+  const bool fp8 = use_tc && use_fused() && use_fp8();
   if (use_tc) {
     float *t1, *t2, *t3, *t4;
     if (ws_get(h, "s16", (size_t)B * T * S, &t4)) return 1;
@@ -1199,6 +1267,17 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
     tc::to_hl16_kernel<<<dim3((T + 31) / 32, (CI + 31) / 32, B), 256, 0, st>>>(cup, c16, B, CI, T);
     lx.check();
     lx.end();
+    if (fp8) {
+      float *u1, *u2, *u3;
+      if (ws_get(h, "h8", (size_t)B * T * R / 2, &u1) || ws_get(h, "h8b", (size_t)B * T * R / 2, &u2) ||
+          ws_get(h, "c8", (size_t)B * T * CI / 2, &u3)) return 1;
+      h8 = (uint8_t*)u1; h8b = (uint8_t*)u2; c8 = (uint8_t*)u3;
+      if (make_tmap_q8(&tm_h8, h8, B, T, R) || make_tmap_q8(&tm_h8b, h8b, B, T, R) || make_tmap_q8(&tm_c8, c8, B, T, CI)) return 1;
+      lx.begin("to_q8");
+      tc::hl16_to_q8_kernel<<<h->sm_count * 8, 256, 0, st>>>(c16, c8, (long long)B * T * CI);
+      lx.check();
+      lx.end();
+    }
   }
   auto launch_tc = [&](const TcPacked& pk, tc::TcParams& tp) {
     tp.Wimg = pk.Wimg; tp.inv_scale = pk.inv_scale; tp.bias = pk.bias;
@@ -1232,6 +1311,12 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
       launch_tc_t<128>(h, tp, st);
       lx.check();
       lx.end();
+      if (fp8) {
+        lx.begin("to_q8");
+        tc::hl16_to_q8_kernel<<<h->sm_count * 8, 256, 0, st>>>(h16, h8, (long long)B * T * R);
+        lx.check();
+        lx.end();
+      }
     } else {  // h = relu(front_conv(z)) : causal k=32
       lx.begin("front");
       ConvP p = make_conv(fl.front);
@@ -1269,23 +1354,31 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
         bp.skip16 = (i == nb - 1) ? s16 : nullptr;
         static bool attrb[64] = {false};
         if (!attrb[h->device & 63]) {
-          CU_TRY(cudaFuncSetAttribute(tc::tc_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::BLK_SMEM));
-          CU_TRY(cudaFuncSetAttribute(tc::tc_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::BLK_SMEM));
+          CU_TRY(cudaFuncSetAttribute(tc::tc_block_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::BLK_SMEM));
+          CU_TRY(cudaFuncSetAttribute(tc::tc_block_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::BLK_SMEM));
+          CU_TRY(cudaFuncSetAttribute(tc::tc_block_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::BLK_SMEM));
+          CU_TRY(cudaFuncSetAttribute(tc::tc_block_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::BLK_SMEM));
           attrb[h->device & 63] = true;
         }
         const long long tiles = (long long)bp.t_tiles * B;
         const int grid = (int)std::min<long long>(tiles, h->sm_count);
+        const bool q8 = fp8 && fl.has_tc_front && fl.tc_gate[i].Wimg8;
+        if (q8) { bp.tmH8 = tm_h8; bp.tmC8 = tm_c8; bp.W1q = fl.tc_gate[i].Wimg8; bp.h8_out = h8b; }
         if (block_stats_on()) {   // instrumented build: wait cycles of CTA 0 per barrier, printed by block_stats_dump()
           bp.stats = block_stats_buf();
-          tc::tc_block_kernel<true><<<grid, tc::NUM_THREADS, tc::BLK_SMEM, st>>>(bp);
+          if (q8) tc::tc_block_kernel<true, true><<<grid, tc::NUM_THREADS, tc::BLK_SMEM, st>>>(bp);
+          else tc::tc_block_kernel<true, false><<<grid, tc::NUM_THREADS, tc::BLK_SMEM, st>>>(bp);
+        } else if (q8) {
+          tc::tc_block_kernel<false, true><<<grid, tc::NUM_THREADS, tc::BLK_SMEM, st>>>(bp);
         } else {
-          tc::tc_block_kernel<false><<<grid, tc::NUM_THREADS, tc::BLK_SMEM, st>>>(bp);
+          tc::tc_block_kernel<false, false><<<grid, tc::NUM_THREADS, tc::BLK_SMEM, st>>>(bp);
         }
         lx.check();
         lx.end();
         std::swap(h16, h16b);          // the block's output is the next block's input
         std::swap(tm_h, tm_hb);
         std::swap(tm_h32, tm_hb32);
+        if (fp8) { std::swap(h8, h8b); std::swap(tm_h8, tm_h8b); }
         continue;
       }
       if (use_tc) {

@@ -41,6 +41,10 @@ struct BlockParams {
                                  // so it must not be updated in place: the unfused pair had a kernel boundary in between)
   __half* h_out16;               // residual stream of the block OUTPUT (ping-pong buffer)
   float* skip; int skip_set; __half* skip16; float scale;
+  // ---- Q8 build only: GEMM1's two correction passes on 8-bit operands ----
+  CUtensorMap tmH8, tmC8;        // uint8 planes [2B][T][C]: plane 0 = e4m3(a_hi), plane 1 = e5m2(16 a_lo); boxes 32 B x 128 rows
+  const uint8_t* W1q;            // gate images [2 n-tiles][nch1][32 KB]: w_hi fp16 (SW64) | e4m3(w_lo) | e4m3(w_hi/16) (SW32)
+  uint8_t* h8_out;               // 8-bit planes of the block OUTPUT (the next block's A operand)
   unsigned long long* stats;     // STATS build only: wait-cycle counters of CTA 0 (CUBE_BLOCK_STATS=1), 24 slots
 };
 
@@ -57,7 +61,7 @@ struct BlockParams {
   } while (0)
 
 // 18 warps: the SM sub-partitions hold 5,5,4,4 of them, so 16384/5 -> 96 registers per thread is the hardware cap
-template <bool STATS>
+template <bool STATS, bool Q8>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_constant__ BlockParams p) {
   long long st_acc[STATS ? 8 : 1] = {0};
   const long long st_begin = STATS ? clock64() : 0;
@@ -92,6 +96,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
     for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(&hbar[w], 1);
     prefetch_tmap(&p.tmHin32);
     prefetch_tmap(&p.tmHout32);
+    if (Q8) { prefetch_tmap(&p.tmH8); prefetch_tmap(&p.tmC8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -129,10 +134,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
               mbar_expect_tx(&full[st], BLK_STAGE_BYTES);
               const CUtensorMap* tm = cond ? &p.tmC : &p.tmH;
               tma_load_3d(sb, tm, &full[st], cc * BK, row, b);
-              tma_load_3d(sb + A_TILE_BYTES, tm, &full[st], cc * BK, row, p.B + b);
-              const __half* wc = wt + (size_t)chunk * 2 * (BN * BK);
-              bulk_load(sb + 2 * A_TILE_BYTES, wc, B_BYTES, &full[st]);
-              bulk_load(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, &full[st]);
+              if constexpr (Q8) {
+                // a_hi fp16 (8 KB) | e4m3(a_hi) (4 KB) | e5m2(16 a_lo) (4 KB); one 32 KB weight image
+                const CUtensorMap* tm8 = cond ? &p.tmC8 : &p.tmH8;
+                tma_load_3d(sb + A_TILE_BYTES, tm8, &full[st], cc * BK, row, b);
+                tma_load_3d(sb + A_TILE_BYTES + A_TILE_BYTES / 2, tm8, &full[st], cc * BK, row, p.B + b);
+                bulk_load(sb + 2 * A_TILE_BYTES, p.W1q + ((size_t)nt * nch1 + chunk) * (2 * B_BYTES), 2 * B_BYTES, &full[st]);
+              } else {
+                tma_load_3d(sb + A_TILE_BYTES, tm, &full[st], cc * BK, row, p.B + b);
+                const __half* wc = wt + (size_t)chunk * 2 * (BN * BK);
+                bulk_load(sb + 2 * A_TILE_BYTES, wc, B_BYTES, &full[st]);
+                bulk_load(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, &full[st]);
+              }
             }
           }
         }
@@ -179,12 +192,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
               const uint32_t a_hi = smem_u32(smem + st * BLK_STAGE_BYTES), a_lo = a_hi + A_TILE_BYTES;
               const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + B_BYTES;
               const int ksteps = (cond && cc == ncc - 1) ? p.c_last_ksteps : (BK / 16);
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t ko = ks * 32;
-                umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
-                umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
-                umma_f16(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
-                accumulate = 1;
+              if constexpr (Q8) {
+                // hi*hi in fp16 (K = 16 per MMA), then the two 2^-11-weight corrections as ONE 8-bit MMA each (K = 32):
+                // e4m3(a_hi) x e4m3(w_lo)  and  e5m2(16 a_lo) x e4m3(w_hi / 16)  -> 4 MMAs per chunk instead of 6
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  umma_f16(d_tmem, make_desc(a_hi + ks * 32), make_desc(b_hi + ks * 32), idesc, accumulate);
+                  accumulate = 1;
+                }
+                const uint32_t a8_hi = a_hi + A_TILE_BYTES, a8_lo = a8_hi + A_TILE_BYTES / 2;
+                const uint32_t b8_lo = b_hi + B_BYTES, b8_hi = b8_lo + B_BYTES / 2;
+                umma_f8(d_tmem, make_desc32(a8_hi), make_desc32(b8_lo), make_idesc_f8(BN, BM, 0), 1);
+                umma_f8(d_tmem, make_desc32(a8_lo), make_desc32(b8_hi), make_idesc_f8(BN, BM, 1), 1);
+              } else {
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  const uint32_t ko = ks * 32;
+                  umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
+                  umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+                  umma_f16(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                  accumulate = 1;
+                }
               }
               umma_commit(&empty[st]);
             }
@@ -406,6 +432,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
             const float n0 = valid ? ((oh.x + ol.x) + v0) * p.scale : 0.f;
             const float n1 = valid ? ((oh.y + ol.y) + v1) * p.scale : 0.f;
             split16x2(n0, n1, hi2[j >> 1], lo2[j >> 1]);
+          }
+          if constexpr (Q8) {      // the next block's 8-bit A planes of these 16 channels (16 bytes per plane and row)
+            if (in_range) {
+              uint32_t qh[8], ql[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) q8_pair(hi2[j], lo2[j], qh[j], ql[j]);
+              uint8_t* d8 = p.h8_out + ((size_t)b * p.T + t) * 128 + cc;
+              *reinterpret_cast<uint4*>(d8) = make_uint4(qh[0] | (qh[1] << 16), qh[2] | (qh[3] << 16), qh[4] | (qh[5] << 16), qh[6] | (qh[7] << 16));
+              *reinterpret_cast<uint4*>(d8 + plane) = make_uint4(ql[0] | (ql[1] << 16), ql[2] | (ql[3] << 16), ql[4] | (ql[5] << 16), ql[6] | (ql[7] << 16));
+            }
           }
           *reinterpret_cast<uint4*>(piece_hi + off0) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
           *reinterpret_cast<uint4*>(piece_hi + off1) = make_uint4(hi2[4], hi2[5], hi2[6], hi2[7]);

@@ -17,6 +17,7 @@
 // epilogue (TMEM -> registers -> global; four warps per TMEM lane quarter, a quarter of the columns each).  Persistent CTAs, 2-stage smem ring of 96 KB stages,
 // double-buffered 2 x 256-column fp32 accumulators in TMEM.
 #pragma once
+#include <cuda_fp8.h>
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -287,6 +288,42 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 // instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n
 __host__ __device__ constexpr uint32_t make_idesc(int n, int m = BM) {
   return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- 8-bit correction passes (tc_block_kernel<.., Q8 = true>): a_hi*w_lo and a_lo*w_hi carry a 2^-11 weight, so their
+// operands may be e4m3 / e5m2 (kind::f8f6f4, K = 32 per instruction: twice the fp16 rate); see
+// profiles/r1_split_precision_study.md.  Tiles are [rows][32 bytes] K-major, SWIZZLE_32B.
+// byte offset of (row r, byte k) inside such a tile
+__host__ __device__ constexpr int swz32_off(int r, int k) { return r * 32 + ((((k >> 4) & 1) ^ ((r >> 2) & 1)) << 4) + (k & 15); }
+__device__ __forceinline__ uint64_t make_desc32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                 // LBO (unused for swizzled K-major)
+  d |= (uint64_t)((8 * 32) >> 4) << 32;   // SBO between 8-row groups of 32-byte rows
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)6 << 61;                 // SWIZZLE_32B
+  return d;
+}
+// instruction descriptor for kind::f8f6f4: D = f32, B = e4m3, A = e4m3 (a_e5m2 = 0) or e5m2 (1), both K-major
+__host__ __device__ constexpr uint32_t make_idesc_f8(int n, int m, int a_e5m2) {
+  return (1u << 4) | ((uint32_t)a_e5m2 << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the two 8-bit planes of an activation stored as fp16 (hi, lo): e4m3(hi) and e5m2(16 * lo); two values per call
+__device__ __forceinline__ void q8_pair(uint32_t hi2, uint32_t lo2, uint32_t& q_hi, uint32_t& q_lo) {
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+  const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lo2));
+  q_hi = __nv_cvt_float2_to_fp8x2(h, __NV_SATFINITE, __NV_E4M3);                                   // low byte = .x
+  q_lo = __nv_cvt_float2_to_fp8x2(make_float2(l.x * 16.f, l.y * 16.f), __NV_SATFINITE, __NV_E5M2);
 }
 
 __device__ __forceinline__ __half f2h_sat(float x) {
@@ -942,6 +979,19 @@ __global__ void __launch_bounds__(256) taps_to_hl16_kernel(const float* __restri
     }
     reinterpret_cast<uint4*>(dst)[i] = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
     reinterpret_cast<uint4*>(dst + plane)[i] = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
+  }
+}
+
+// fp16 (hi, lo) planes [2][n] -> 8-bit planes [2][n]: e4m3(hi), e5m2(16 lo); 8 elements per thread and step
+__global__ void __launch_bounds__(256) hl16_to_q8_kernel(const __half* __restrict__ src, uint8_t* __restrict__ dst, long long n) {
+  const long long n8 = n / 8;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
+    const uint4 h = reinterpret_cast<const uint4*>(src)[i];
+    const uint4 l = reinterpret_cast<const uint4*>(src + n)[i];
+    uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+    q8_pair(h.x, l.x, a0, b0); q8_pair(h.y, l.y, a1, b1); q8_pair(h.z, l.z, a2, b2); q8_pair(h.w, l.w, a3, b3);
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(a0 | (a1 << 16), a2 | (a3 << 16));
+    reinterpret_cast<uint2*>(dst + n)[i] = make_uint2(b0 | (b1 << 16), b2 | (b3 << 16));
   }
 }
 
