@@ -148,18 +148,27 @@ def best_cpu_threads(arch, weights):
     return best, best_rate
 
 
-def cpu_oracle_rate(arch, weights, frames, threads):
-    """Time the CPU oracle port on B=1 x `frames`; returns (samples/s, samples, seconds)."""
+def cpu_oracle_rate(arch, weights, frames, threads, batch=1):
+    """Time the CPU oracle port on `batch` x `frames`; returns (samples/s, samples, seconds)."""
     from oracle import clarinet_ref as C, hifigan_ref as H
     torch.set_num_threads(threads)
-    mel, z = synth_inputs(arch, 1, frames, seed=99)
+    mel, z = synth_inputs(arch, batch, frames, seed=99)
     t0 = time.perf_counter()
     if arch == "student":
         y = C.vocode_student(weights[0], weights[1], mel, z)
     else:
         y = H.generator_forward(weights[0], weights[1], mel)
     dt = time.perf_counter() - t0
-    return y.shape[-1] / dt, int(y.shape[-1]), dt
+    n = int(y.shape[-1]) * batch
+    return n / dt, n, dt
+
+
+def cpu_sample_shape(rate, F, hop, seconds):
+    """(batch, frames) of a CPU sample worth about `seconds` at `rate` samples/s: full-length utterances first, then more of them"""
+    want = max(8 * hop, rate * seconds)
+    frames = int(max(8, min(F, want / hop)))
+    batch = int(max(1, min(16, want // (frames * hop))))
+    return batch, frames
 
 
 def run_reference(args, arch, B, F, desc, rank, world):
@@ -171,15 +180,15 @@ def run_reference(args, arch, B, F, desc, rank, world):
     rate, _, _ = cpu_oracle_rate(arch, weights, 48 if arch == "student" else 96, threads)  # probe at a realistic length
     budget = min(10.0, 120.0 / max(1, args.steps + args.warmup))
     hop = 256 if arch == "student" else 240
-    frames = int(max(8, min(F, 0.7 * rate * budget / hop)))
+    cb, frames = cpu_sample_shape(0.7 * rate, F, hop, budget)
     for _ in range(args.warmup):
-        cpu_oracle_rate(arch, weights, frames, threads)
+        cpu_oracle_rate(arch, weights, frames, threads, cb)
     tot_s, tot_t = 0, 0.0
     for _ in range(args.steps):
-        _, n, dt = cpu_oracle_rate(arch, weights, frames, threads)
+        _, n, dt = cpu_oracle_rate(arch, weights, frames, threads, cb)
         tot_s += n; tot_t += dt
     val = tot_s / tot_t
-    sample = (f"B=1 x {frames} frames ({frames * hop / SR:.2f} s of audio) per step of the same synthetic workload; oracle port "
+    sample = (f"B={cb} x {frames} frames ({cb * frames * hop / SR:.2f} s of audio) per step of the same synthetic workload; oracle port "
               f"(torch CPU fp32), {threads} threads = fastest of a sweep on a {os.cpu_count()}-core host")
     line = {
         "impl": "reference", "metric": "audio samples/sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
@@ -425,10 +434,10 @@ def main():
         threads, _ = best_cpu_threads(arch, weights)
         rate, _, _ = cpu_oracle_rate(arch, weights, 48 if arch == "student" else 96, threads)
         hop = 256 if arch == "student" else 240
-        frames = int(max(8, min(F, 0.7 * rate * 15.0 / hop)))
-        r2, n, dt = cpu_oracle_rate(arch, weights, frames, threads)
+        cb, frames = cpu_sample_shape(0.7 * rate, F, hop, 15.0)
+        r2, n, dt = cpu_oracle_rate(arch, weights, frames, threads, cb)
         cpu = {"value": r2, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": f"B=1 x {frames} frames ({n} samples, {dt:.1f} s of CPU) of the same synthetic workload; oracle port, torch CPU fp32, {threads} threads"}
+               "sample": f"B={cb} x {frames} frames ({n} samples, {dt:.1f} s of CPU) of the same synthetic workload; oracle port, torch CPU fp32, {threads} threads"}
 
     line = {
         "metric": "audio samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
