@@ -396,21 +396,25 @@ def main():
         flops_launch = (BLOCK_FLOPS if fused else GATE_FLOPS) * samples_per_step
         ach = flops_launch * nlaunch / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else None
         roof = {"kernel": "conv_tile_kernel<8,8,8,1> EPI_GATE (gated dilated conv k3 128->2x256 + conditioning 1x1 80->2x256, fp32 FFMA2)" if math == 0
-                else ("tc::tc_block_kernel (whole residual block: gated dilated conv + conditioning 1x1 -> o kept in smem -> res/skip 1x1; "
-                      "tcgen05 UMMA 128x256x16 f16, split-fp16 x3, TMA taps)" if fused else
+                else ("tc::tc_block_pair_kernel (whole residual block on a CTA pair: gated dilated conv + conditioning 1x1 -> o kept in smem "
+                      "-> res/skip 1x1; tcgen05 cta_group::2 UMMA 256x256, hi*hi in fp16 + two 8-bit correction passes in GEMM1, TMA taps; "
+                      "CUBE_TC_PAIR=0 / CUBE_TC_FP8=0 select the single-CTA / three-fp16-pass variants)" if fused else
                       "tc::tc_conv_kernel TC_EPI_GATE (same layer on tcgen05: UMMA 128x256x16 f16, split-fp16 x3, TMA taps)"),
                 "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                 "frac": (ach / pk["tf_sust"]) if ach else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, round 1
                 # (profiles/r1_ncu_full_tc_conv.md: 1.52 GB + 1.79 GB); only valid for the default geometry
+                # ncu capture of the single-CTA three-pass kernel (the pair kernel moves the same DRAM bytes: same tensors)
                 "traffic": (FUSED_TRAFFIC if fused else 3.31e9) if (math == 1 and B == 8 and F == 862) else None,
-                "traffic_source": ("profiles/r1_ncu_full_tc_block.md (ncu --set full, one tc_block_kernel launch)" if fused else
+                "traffic_source": ("profiles/r1_ncu_full_tc_block.md (ncu --set full, one tc_block_kernel launch, single-CTA variant)" if fused else
                                    "profiles/r1_ncu_full_tc_conv.md (ncu --set full, gate launch)"),
                 "launches_per_step": nlaunch, "avg_launch_ms": dom_ms / max(1, nlaunch),
                 "algorithmic_flops_per_launch": flops_launch, "algorithmic_bytes_per_launch": (BLOCK_BYTES if fused else GATE_BYTES) * samples_per_step,
                 "share_of_step": dom_ms / (ms / args.steps) if ms > 0 else None,
                 "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
-                "math": "fp32 FFMA (no tensor cores)" if math == 0 else "tcgen05 split-fp16 x3"}
+                "math": "fp32 FFMA (no tensor cores)" if math == 0 else
+                        ("tcgen05: fp16 hi*hi + 2 x 8-bit correction passes (GEMM1), split-fp16 x3 (GEMM2)"
+                         if fused and os.environ.get("CUBE_TC_FP8", "1") != "0" else "tcgen05 split-fp16 x3")}
         whole = {"flops_per_sample": PWN_FLOPS_PER_SAMPLE, "bytes_per_sample": PWN_BYTES_PER_SAMPLE}
     else:
         dom = "rb_conv1"

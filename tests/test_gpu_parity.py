@@ -11,9 +11,10 @@ from oracle import clarinet_ref as C, heads_ref as W, hifigan_ref as H
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
 MATHS = [pytest.param(0, id="fp32_simt"), pytest.param(1, id="tcgen05_split16")]
-# CUBE_TC_FP8=1 (8-bit correction passes in the student's block kernel): still inside the 1e-3 budget, but no longer at
-# fp32 round-off - the CPU emulation (profiles/r1_split_precision_study.md) predicts 3e-5 .. 5e-5
-FP8 = __import__("os").environ.get("CUBE_TC_FP8") == "1"
+# The student's default tensor-core path runs GEMM1's two correction passes on 8-bit operands (CUBE_TC_FP8, default on):
+# inside the 1e-3 budget with a 20-40x margin, but no longer at fp32 round-off - the CPU emulation
+# (profiles/r1_split_precision_study.md) predicts 3e-5 .. 5e-5.  CUBE_TC_FP8=0 (three fp16 passes) is held to the tight bounds.
+FP8 = __import__("os").environ.get("CUBE_TC_FP8", "1") != "0"
 
 
 @pytest.fixture(scope="module")
@@ -490,7 +491,9 @@ def test_mel_copy_synthesis_chain(dev, neb):
     pytest.param({"CUBE_TC_FUSED": "0"}, "student and tcgen05", id="student_unfused_pair"),
     pytest.param({"CUBE_TC_FUSED": "0", "CUBE_TC_CG2": "1"}, "student and tcgen05 and not full_length", id="student_cta_pair"),
     pytest.param({"CUBE_TC_WIN": "0"}, "hifigan and tcgen05 and not full_size and not loudness", id="hifigan_no_window"),
-    pytest.param({"CUBE_TC_FP8": "1"}, "student and tcgen05", id="student_fp8_corrections"),
+    pytest.param({"CUBE_TC_FP8": "0"}, "student and tcgen05", id="student_pair_fp16x3"),
+    pytest.param({"CUBE_TC_FP8": "0", "CUBE_TC_PAIR": "0"}, "student and tcgen05", id="student_single_cta_fp16x3"),
+    pytest.param({"CUBE_TC_PAIR": "0"}, "student and tcgen05 and not full_length", id="student_single_cta_fp8"),
 ])
 def test_variants_in_subprocess(env, select):
     """The library reads its kernel-selection switches once per process, so the non-default variants (gate + res/skip

@@ -1,0 +1,470 @@
+// CTA-PAIR version of the fused ClariNet residual block (tc_block.cuh): two CTAs of a cluster compute a 256-row tile with
+// tcgen05.mma.cta_group::2 (M = 256).  Each CTA stages its own 128 rows of A (and holds its own rows of o, h, skip:
+// epilogues are unchanged) but only HALF of every weight tile - the pair's tensor cores exchange the halves - so the
+// L2 -> shared-memory traffic per output row drops by a third and a stage shrinks to 32 KB (4 stages instead of 3).
+// Roles: the leader's (rank 0) MMA thread issues every MMA of the pair and owns the accumulator / o-buffer hand-shakes
+// (the peer's epilogue warps arrive remotely on the leader's barriers; tcgen05.commit multicasts the completions to
+// both CTAs); the peer's MMA warp only relays "my stage has landed".  Opt-in: CUBE_TC_PAIR=1.
+// THIS FILE IS GENERATED FROM tc_block.cuh's kernel text by a mechanical transformation (see git history) and then
+// maintained by hand; keep the two in step.
+#pragma once
+#include "tc_block.cuh"
+
+namespace cube {
+namespace tc {
+
+constexpr int PAIR_STAGES = 4;
+constexpr int PAIR_STAGE_BYTES = 2 * A_TILE_BYTES + 2 * (128 * BK * 2);      // 32 KB
+constexpr int PAIR_SMEM = PAIR_STAGES * PAIR_STAGE_BYTES + BLK_O_BYTES + 1024 + 512 + 768 * 8;
+
+__device__ __forceinline__ void umma_f8_2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// epilogue -> leader's MMA thread: local arrive on the leader, remote (relaxed, cluster scope) from the peer
+__device__ __forceinline__ void pair_arrive(uint64_t* bar, uint32_t crank) {
+  if (crank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0);
+}
+
+template <bool Q8>
+__global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_pair_kernel(const __grid_constant__ BlockParams p) {
+  constexpr bool STATS = false;                    // (the instrumented build exists for the 1-CTA kernel only)
+  long long st_acc[1] = {0};
+  const long long st_begin = 0;
+  (void)st_acc; (void)st_begin;
+  constexpr int BN = 256;
+  constexpr int B_BYTES = (BN / 2) * BK * 2;       // this CTA's HALF of the weight tile: 8 KB per fp16 plane
+  constexpr int NST = PAIR_STAGES;
+  constexpr int STG = PAIR_STAGE_BYTES;            // A 16 KB + W half 16 KB
+  const uint32_t crank = cluster_ctarank();        // 0 = leader: issues the pair's MMAs
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* o_smem = smem + NST * STG;      // [4 chunks][hi 8 KB | lo 8 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(o_smem + BLK_O_BYTES);
+  uint64_t* full = bars;                       // [4] this CTA's stage has landed
+  uint64_t* empty = bars + NST;                // [4] (commit multicast: both CTAs)
+  uint64_t* pfull = bars + 2 * NST;            // [4] leader only: the PEER's stage has landed (relayed by its MMA warp)
+  uint64_t* acc_full = bars + 3 * NST;         // [2] region holds a finished accumulator        (commit multicast -> both epilogues)
+  uint64_t* acc_free = acc_full + 2;           // [2] leader only: region drained by BOTH CTAs   (2 x 16 warps)
+  uint64_t* o_full = acc_free + 2;             // [1] leader only: o half staged in BOTH CTAs    (2 x 16 warps)
+  uint64_t* o_free = o_full + 1;               // [1] GEMM2 has read the o half                  (MMA -> epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+  uint64_t* hbar = o_free + 2;                 // [16] per epilogue warp: its residual rows have landed in shared memory
+  float2* sb1 = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [512] gate: folded exp2 factors
+  float2* sb2 = sb1 + 512;                                                           // [256] res/skip
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.t_tiles * p.B;
+  const int nch1 = p.taps * p.h_chunks + p.c_chunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmH);
+    prefetch_tmap(&p.tmC);
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&pfull[s], 1); }
+    for (int r = 0; r < 2; ++r) { mbar_init(&acc_full[r], 1); mbar_init(&acc_free[r], 2 * NUM_EPI_WARPS); }
+    mbar_init(o_full, 2 * NUM_EPI_WARPS);
+    mbar_init(o_free, 1);
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(&hbar[w], 1);
+    prefetch_tmap(&p.tmHin32);
+    prefetch_tmap(&p.tmHout32);
+    if (Q8) { prefetch_tmap(&p.tmH8); prefetch_tmap(&p.tmC8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, 512);
+  {  // folded per-column constants, once per CTA (this CTA owns all 512 + 256 columns)
+    constexpr float LOG2E = 1.4426950408889634f;
+    for (int i = threadIdx.x; i < 512; i += NUM_THREADS) {
+      const float k = (i & 255) < 128 ? 2.f * LOG2E : -LOG2E;     // filter cols -> e^{2f}, gate cols -> e^{-g}
+      sb1[i] = make_float2(__ldg(p.inv1 + i) * k, __ldg(p.bias1 + i) * k);
+    }
+    for (int i = threadIdx.x; i < 256; i += NUM_THREADS) sb2[i] = make_float2(__ldg(p.inv2 + i), __ldg(p.bias2 + i));
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                        // both CTAs' barriers are initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x >> 1; tile < total_tiles; tile += gridDim.x >> 1) {
+        const int tt = tile % p.t_tiles, b = tile / p.t_tiles;
+        const int t0 = tt * 2 * BM + (int)crank * BM;          // this CTA's 128 rows of the pair's 256-row tile
+        for (int nt = 0; nt < 2; ++nt) {                       // GEMM1, one 256-column n-tile at a time
+          const __half* wt = p.W1 + (size_t)nt * nch1 * 2 * (BN * BK);
+          int chunk = 0;
+          for (int tap = 0; tap <= p.taps; ++tap) {            // tap == p.taps: the conditioning segment
+            const bool cond = tap == p.taps;
+            const int row = cond ? t0 : t0 + p.off0 + tap * p.dil;
+            const int ncc = cond ? p.c_chunks : p.h_chunks;
+            for (int cc = 0; cc < ncc; ++cc, ++chunk, ++it) {
+              const int st = it % NST;
+              BLK_WAIT(&empty[st], ((it / NST) & 1) ^ 1, 0);
+              uint8_t* sb = smem + st * STG;
+              mbar_expect_tx(&full[st], STG);
+              const CUtensorMap* tm = cond ? &p.tmC : &p.tmH;
+              tma_load_3d(sb, tm, &full[st], cc * BK, row, b);
+              if constexpr (Q8) {
+                // a_hi fp16 (8 KB) | e4m3(a_hi) (4 KB) | e5m2(16 a_lo) (4 KB); one 32 KB weight image
+                const CUtensorMap* tm8 = cond ? &p.tmC8 : &p.tmH8;
+                tma_load_3d(sb + A_TILE_BYTES, tm8, &full[st], cc * BK, row, b);
+                tma_load_3d(sb + A_TILE_BYTES + A_TILE_BYTES / 2, tm8, &full[st], cc * BK, row, p.B + b);
+                // rows [128 crank, +128) of each of the three sub-images of the 32 KB chunk image
+                const uint8_t* wq = p.W1q + ((size_t)nt * nch1 + chunk) * 32768;
+                bulk_load(sb + 2 * A_TILE_BYTES, wq + crank * B_BYTES, B_BYTES, &full[st]);
+                bulk_load(sb + 2 * A_TILE_BYTES + B_BYTES, wq + 16384 + crank * (B_BYTES / 2), B_BYTES / 2, &full[st]);
+                bulk_load(sb + 2 * A_TILE_BYTES + B_BYTES + B_BYTES / 2, wq + 24576 + crank * (B_BYTES / 2), B_BYTES / 2, &full[st]);
+              } else {
+                tma_load_3d(sb + A_TILE_BYTES, tm, &full[st], cc * BK, row, p.B + b);
+                const __half* wc = wt + (size_t)chunk * 2 * (BN * BK) + (size_t)crank * (BN / 2) * BK;   // this CTA's 128 weight rows
+                bulk_load(sb + 2 * A_TILE_BYTES, wc, B_BYTES, &full[st]);
+                bulk_load(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, &full[st]);
+              }
+            }
+          }
+        }
+        for (int ch = 0; ch < 8; ++ch, ++it) {                 // GEMM2: weights only (its A operand is o, on chip)
+          const int st = it % NST;
+          BLK_WAIT(&empty[st], ((it / NST) & 1) ^ 1, 1);
+          uint8_t* sb = smem + st * STG;
+          mbar_expect_tx(&full[st], 2 * B_BYTES);
+          const __half* wc = p.W2 + (size_t)ch * 2 * (BN * BK) + (size_t)crank * (BN / 2) * BK;
+          bulk_load(sb + 2 * A_TILE_BYTES, wc, B_BYTES, &full[st]);
+          bulk_load(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, &full[st]);
+        }
+      }
+      if (STATS && p.stats && blockIdx.x == 0) {
+        atomicAdd(p.stats + 0, (unsigned long long)st_acc[0]);
+        atomicAdd(p.stats + 1, (unsigned long long)st_acc[1]);
+        atomicAdd(p.stats + 2, (unsigned long long)(clock64() - st_begin));
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0 && crank != 0) {
+      // peer CTA: it issues no MMA; this thread relays "my stage has landed" to the leader
+      uint32_t it = 0;
+      for (int tile = blockIdx.x >> 1; tile < total_tiles; tile += gridDim.x >> 1)
+        for (int n = 2 * nch1 + 8; n > 0; --n, ++it) {
+          const int st = it % NST;
+          mbar_wait(&full[st], (it / NST) & 1);
+          mbar_arrive_remote(&pfull[st], 0);
+        }
+    } else if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, 2 * BM);       // M = 256 across the pair
+      uint32_t it = 0, titer = 0;
+      uint32_t free_ph[2] = {0, 0};        // completed-phase counters of acc_free[r] this thread has consumed
+      uint32_t ofull_ph = 0;
+      for (int tile = blockIdx.x >> 1; tile < total_tiles; tile += gridDim.x >> 1, ++titer) {
+        const int r0 = titer & 1, r1 = r0 ^ 1;      // region roles of this tile
+        for (int nt = 0; nt < 2; ++nt) {
+          const int rg = nt == 0 ? r0 : r1;
+          // the region must have been drained by its previous user (first use of each region: passes at once)
+          BLK_WAIT(&acc_free[rg], (free_ph[rg] & 1) ^ 1, nt);
+          ++free_ph[rg];
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + rg * BN;
+          uint32_t accumulate = 0;
+          for (int tap = 0; tap <= p.taps; ++tap) {
+            const bool cond = tap == p.taps;
+            const int ncc = cond ? p.c_chunks : p.h_chunks;
+            for (int cc = 0; cc < ncc; ++cc, ++it) {
+              const int st = it % NST;
+              BLK_WAIT(&full[st], (it / NST) & 1, 2);
+              mbar_wait(&pfull[st], (it / NST) & 1);
+              tc_fence_after();
+              const uint32_t a_hi = smem_u32(smem + st * STG), a_lo = a_hi + A_TILE_BYTES;
+              const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + B_BYTES;
+              const int ksteps = (cond && cc == ncc - 1) ? p.c_last_ksteps : (BK / 16);
+              if constexpr (Q8) {
+                // hi*hi in fp16 (K = 16 per MMA), then the two 2^-11-weight corrections as ONE 8-bit MMA each (K = 32):
+                // e4m3(a_hi) x e4m3(w_lo)  and  e5m2(16 a_lo) x e4m3(w_hi / 16)  -> 4 MMAs per chunk instead of 6
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  umma_f16_2(d_tmem, make_desc(a_hi + ks * 32), make_desc(b_hi + ks * 32), idesc, accumulate);
+                  accumulate = 1;
+                }
+                const uint32_t a8_hi = a_hi + A_TILE_BYTES, a8_lo = a8_hi + A_TILE_BYTES / 2;
+                const uint32_t b8_lo = b_hi + B_BYTES, b8_hi = b8_lo + B_BYTES / 2;
+                umma_f8_2(d_tmem, make_desc32(a8_hi), make_desc32(b8_lo), make_idesc_f8(BN, 2 * BM, 0), 1);
+                umma_f8_2(d_tmem, make_desc32(a8_lo), make_desc32(b8_hi), make_idesc_f8(BN, 2 * BM, 1), 1);
+              } else {
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  const uint32_t ko = ks * 32;
+                  umma_f16_2(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
+                  umma_f16_2(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+                  umma_f16_2(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                  accumulate = 1;
+                }
+              }
+              umma_commit_2(&empty[st]);
+            }
+          }
+          umma_commit_2(&acc_full[rg]);
+        }
+        // GEMM2 into r0 (drained by the gate epilogue of n-tile 0): K half kh uses the o half the epilogue staged
+        {
+          BLK_WAIT(&acc_free[r0], (free_ph[r0] & 1) ^ 1, 3);
+          ++free_ph[r0];
+          const uint32_t d_tmem = tmem_base + r0 * BN;
+          uint32_t accumulate = 0;
+          for (int kh = 0; kh < 2; ++kh) {
+            BLK_WAIT(o_full, ofull_ph & 1, 4 + kh);
+            ++ofull_ph;
+            tc_fence_after();
+            for (int c4 = 0; c4 < 4; ++c4, ++it) {
+              const int st = it % NST;
+              BLK_WAIT(&full[st], (it / NST) & 1, 6);
+              mbar_wait(&pfull[st], (it / NST) & 1);
+              tc_fence_after();
+              const uint32_t a_hi = smem_u32(o_smem + c4 * 2 * A_TILE_BYTES), a_lo = a_hi + A_TILE_BYTES;
+              const uint32_t b_hi = smem_u32(smem + st * STG) + 2 * A_TILE_BYTES, b_lo = b_hi + B_BYTES;
+              for (int ks = 0; ks < BK / 16; ++ks) {
+                const uint32_t ko = ks * 32;
+                umma_f16_2(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
+                umma_f16_2(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+                umma_f16_2(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                accumulate = 1;
+              }
+              umma_commit_2(&empty[st]);
+            }
+            umma_commit_2(o_free);          // the o half may be overwritten
+          }
+          umma_commit_2(&acc_full[r0]);     // r|s accumulator complete
+        }
+      }
+      if (STATS && p.stats && blockIdx.x == 0) {
+        for (int i = 0; i < 7; ++i) atomicAdd(p.stats + 3 + i, (unsigned long long)st_acc[i]);
+        atomicAdd(p.stats + 10, (unsigned long long)(clock64() - st_begin));
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 2..17) ===========================
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int grp = (warp - 2) >> 2;        // 0..3
+    const int row = q * 32 + lane;
+    uint32_t titer = 0;
+    uint32_t full_ph[2] = {0, 0};           // uses of acc_full[r] consumed so far
+    uint32_t ofree_ph = 0;
+    for (int tile = blockIdx.x >> 1; tile < total_tiles; tile += gridDim.x >> 1, ++titer) {
+      const int tt = tile % p.t_tiles, b = tile / p.t_tiles;
+      const int t = tt * 2 * BM + (int)crank * BM + row;
+      const int r0 = titer & 1, r1 = r0 ^ 1;
+      const int len = p.lens ? min(p.lens[b], p.T) : p.T;
+      const bool in_range = t < p.T, valid = t < len;
+      // a flow's last block reads the running skip total: pull this warp's slice into L2 while the MMAs run
+      if (in_range && p.skip16 && !p.skip_set && (lane & 7) == 0) {
+        const float* s0 = p.skip + ((size_t)b * 128 + grp * 32) * p.T + t;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) prefetch_l2(s0 + (size_t)j * p.T);
+      }
+      // ---------------- gate epilogue of n-tile 0 (region r0) and n-tile 1 (region r1) ----------------
+      for (int nt = 0; nt < 2; ++nt) {
+        const int rg = nt == 0 ? r0 : r1;
+        BLK_WAIT(&acc_full[rg], full_ph[rg] & 1, nt);
+        ++full_ph[rg];
+        const long long g_t0 = STATS ? clock64() : 0;
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + rg * BN + ((uint32_t)(q * 32) << 16);
+        const float2* sb = sb1 + nt * 256;
+        // this warp: output channels [32*grp, +32) of this n-tile = K chunk `grp` of the o half
+        uint8_t* otile = o_smem + grp * 2 * A_TILE_BYTES;
+        uint32_t hi2[2][8], lo2[2][8];
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int cc = ci * 16;
+          uint32_t f[16], g[16];
+          tmem_ld16(taddr + grp * 32 + cc, f);
+          tmem_ld16(taddr + 128 + grp * 32 + cc, g);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            float o[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float2 sf = sb[grp * 32 + cc + j + u], sg = sb[128 + grp * 32 + cc + j + u];
+              const float a = fminf(fmaxf(fmaf(__uint_as_float(f[j + u]), sf.x, sf.y), -40.f), 40.f);
+              const float e = fminf(fmaf(__uint_as_float(g[j + u]), sg.x, sg.y), 60.f);
+              const float E1 = ex2_fast(a), E2 = ex2_fast(e);
+              o[u] = valid ? (E1 - 1.f) * rcp_fast((E1 + 1.f) * (1.f + E2)) : 0.f;
+            }
+            split16x2(o[0], o[1], hi2[ci][j >> 1], lo2[ci][j >> 1]);
+          }
+        }
+        // the accumulator region is drained: hand it back before waiting for the o buffer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) pair_arrive(&acc_free[rg], crank);
+        // the o buffer is free once GEMM2 has consumed the previous half (first half ever: passes at once)
+        if (STATS) st_acc[5] += clock64() - g_t0;       // gate math (TMEM load .. region handed back)
+        BLK_WAIT(o_free, (ofree_ph & 1) ^ 1, 2 + nt);
+        ++ofree_ph;
+        if (nt == 0) {   // the residual rows the previous tile stored from this warp's piece of the o buffer have been read
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
+        // K-major SWIZZLE_64B A tile [128 rows][32 ch]: 16-byte piece c16 of row r lives at piece c16 ^ ((r>>1)&3)
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const int c16 = ci * 2 + v;
+            const uint32_t off = row * 64 + ((c16 ^ ((row >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(otile + off) = make_uint4(hi2[ci][4 * v], hi2[ci][4 * v + 1], hi2[ci][4 * v + 2], hi2[ci][4 * v + 3]);
+            *reinterpret_cast<uint4*>(otile + A_TILE_BYTES + off) = make_uint4(lo2[ci][4 * v], lo2[ci][4 * v + 1], lo2[ci][4 * v + 2], lo2[ci][4 * v + 3]);
+          }
+        }
+        fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) pair_arrive(o_full, crank);
+      }
+      // ---------------- res/skip epilogue (GEMM2 result in region r0) ----------------
+      // Every warp owns 32 residual channels [32 grp, +32) and the 32 skip channels of the same index, for its 32 rows.
+      // Measured with CUBE_BLOCK_STATS=1, the read-modify-write of these two streams (not the MMAs) paced the tile
+      // loop: per-row 16-byte global accesses cost 32 L1 wavefronts per instruction, and the next tile's gate
+      // epilogues queue behind them.  So:
+      //  * residual: the warp's [32 rows][32 ch] hi/lo boxes travel by TMA through the warp's own 2 x 2 KB pieces of
+      //    the o buffer (idle once GEMM2 has read it) - load, update in place in the swizzled layout, store;
+      //  * skip (+)= s is a fire-and-forget red.global.add.f32, one 128-byte line per warp instruction (one thread
+      //    per element and launch, so no contention, and the same single round-to-nearest fp32 add a load/add/store
+      //    would do - REDG flushes subnormals, a < 1.2e-38 difference - without a load on the critical path).
+      {
+        const uint32_t taddr_rs = tmem_base + r0 * BN + ((uint32_t)(q * 32) << 16) + grp * 32;
+        const size_t plane = (size_t)p.B * p.T * 128;
+        float* sp0 = p.skip + ((size_t)b * 128 + grp * 32) * p.T + t;
+        const bool last_block = p.skip16 != nullptr;
+        const int ew = warp - 2;
+        uint8_t* piece_hi = o_smem + grp * 2 * A_TILE_BYTES + q * 2048;      // rows [32 q, +32) of K chunk grp
+        uint8_t* piece_lo = piece_hi + A_TILE_BYTES;
+        const int tw = tt * 2 * BM + (int)crank * BM + q * 32;               // first time step of this warp's rows
+        float old[32];             // only a flow's last block needs the running skip total (relu -> fp16 planes)
+        if (last_block) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) old[j] = (in_range && !p.skip_set) ? __ldcs(sp0 + (size_t)j * p.T) : 0.f;
+        }
+        BLK_WAIT(&acc_full[r0], full_ph[r0] & 1, 4);
+        ++full_ph[r0];
+        const long long r_t0 = STATS ? clock64() : 0;
+        tc_fence_after();
+        if (lane == 0) {           // GEMM2 is complete: the o buffer is idle, fetch the residual rows into this warp's pieces
+          mbar_expect_tx(&hbar[ew], 2 * 2048);
+          tma_load_3d(piece_hi, &p.tmHin32, &hbar[ew], grp * 32, tw, b);
+          tma_load_3d(piece_lo, &p.tmHin32, &hbar[ew], grp * 32, tw, p.B + b);
+        }
+        // ---- skip columns [128 + 32 grp, +32) ----
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int cc = grp * 32 + ci * 16;
+          uint32_t racc[16];
+          tmem_ld16(taddr_rs + 128 + ci * 16, racc);
+          tmem_ld_wait();
+          if (last_block) {
+            uint32_t hi2[8], lo2[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const float2 s0 = sb2[128 + cc + j], s1 = sb2[128 + cc + j + 1];
+              const float y0 = old[ci * 16 + j] + fmaf(__uint_as_float(racc[j]), s0.x, s0.y);
+              const float y1 = old[ci * 16 + j + 1] + fmaf(__uint_as_float(racc[j + 1]), s1.x, s1.y);
+              split16x2(valid ? fmaxf(y0, 0.f) : 0.f, valid ? fmaxf(y1, 0.f) : 0.f, hi2[j >> 1], lo2[j >> 1]);
+            }
+            if (in_range) {
+              __half* srow = p.skip16 + ((size_t)b * p.T + t) * 128 + cc;
+#pragma unroll
+              for (int v = 0; v < 2; ++v) {
+                reinterpret_cast<uint4*>(srow)[v] = make_uint4(hi2[4 * v], hi2[4 * v + 1], hi2[4 * v + 2], hi2[4 * v + 3]);
+                reinterpret_cast<uint4*>(srow + plane)[v] = make_uint4(lo2[4 * v], lo2[4 * v + 1], lo2[4 * v + 2], lo2[4 * v + 3]);
+              }
+            }
+          } else if (in_range) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 s2 = sb2[128 + cc + j];
+              const float y = valid ? fmaf(__uint_as_float(racc[j]), s2.x, s2.y) : 0.f;
+              float* dst = sp0 + (size_t)(ci * 16 + j) * p.T;
+              if (p.skip_set) __stcs(dst, y);
+              else asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst), "f"(y) : "memory");
+            }
+          }
+        }
+        // ---- residual columns [32 grp, +32): h_out = (h_in + r) * sqrt(.5), in place in the swizzled pieces ----
+        mbar_wait(&hbar[ew], titer & 1);
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int cc = grp * 32 + ci * 16;
+          uint32_t racc[16];
+          tmem_ld16(taddr_rs + ci * 16, racc);
+          // K-major SWIZZLE_64B: 16-byte piece c16 of row r lives at piece c16 ^ ((r >> 1) & 3) of its 64-byte row
+          const uint32_t off0 = lane * 64 + (((ci * 2) ^ ((lane >> 1) & 3)) << 4);
+          const uint32_t off1 = lane * 64 + (((ci * 2 + 1) ^ ((lane >> 1) & 3)) << 4);
+          uint4 hv[2], lv[2];
+          hv[0] = *reinterpret_cast<const uint4*>(piece_hi + off0);
+          hv[1] = *reinterpret_cast<const uint4*>(piece_hi + off1);
+          lv[0] = *reinterpret_cast<const uint4*>(piece_lo + off0);
+          lv[1] = *reinterpret_cast<const uint4*>(piece_lo + off1);
+          tmem_ld_wait();
+          if (ci == 1) {           // last TMEM read of this warp: hand the region back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) pair_arrive(&acc_free[r0], crank);
+          }
+          const uint32_t* hp = reinterpret_cast<const uint32_t*>(hv);
+          const uint32_t* lp = reinterpret_cast<const uint32_t*>(lv);
+          uint32_t hi2[8], lo2[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float2 s0 = sb2[cc + j], s1 = sb2[cc + j + 1];
+            const float2 oh = unpack_h2(hp[j >> 1]), ol = unpack_h2(lp[j >> 1]);
+            const float v0 = fmaf(__uint_as_float(racc[j]), s0.x, s0.y), v1 = fmaf(__uint_as_float(racc[j + 1]), s1.x, s1.y);
+            const float n0 = valid ? ((oh.x + ol.x) + v0) * p.scale : 0.f;
+            const float n1 = valid ? ((oh.y + ol.y) + v1) * p.scale : 0.f;
+            split16x2(n0, n1, hi2[j >> 1], lo2[j >> 1]);
+          }
+          if constexpr (Q8) {      // the next block's 8-bit A planes of these 16 channels (16 bytes per plane and row)
+            if (in_range) {
+              uint32_t qh[8], ql[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) q8_pair(hi2[j], lo2[j], qh[j], ql[j]);
+              uint8_t* d8 = p.h8_out + ((size_t)b * p.T + t) * 128 + cc;
+              *reinterpret_cast<uint4*>(d8) = make_uint4(qh[0] | (qh[1] << 16), qh[2] | (qh[3] << 16), qh[4] | (qh[5] << 16), qh[6] | (qh[7] << 16));
+              *reinterpret_cast<uint4*>(d8 + plane) = make_uint4(ql[0] | (ql[1] << 16), ql[2] | (ql[3] << 16), ql[4] | (ql[5] << 16), ql[6] | (ql[7] << 16));
+            }
+          }
+          *reinterpret_cast<uint4*>(piece_hi + off0) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
+          *reinterpret_cast<uint4*>(piece_hi + off1) = make_uint4(hi2[4], hi2[5], hi2[6], hi2[7]);
+          *reinterpret_cast<uint4*>(piece_lo + off0) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
+          *reinterpret_cast<uint4*>(piece_lo + off1) = make_uint4(lo2[4], lo2[5], lo2[6], lo2[7]);
+        }
+        fence_proxy_async();       // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {           // rows beyond T are clipped by the tensor map
+          tma_store_3d(&p.tmHout32, piece_hi, grp * 32, tw, b);
+          tma_store_3d(&p.tmHout32, piece_lo, grp * 32, tw, p.B + b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (STATS) st_acc[6] += clock64() - r_t0;     // res/skip epilogue after the accumulator arrived
+      }
+    }
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until the bulk engine has read it
+    if (STATS && p.stats && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 10)) {
+      unsigned long long* o = p.stats + (warp == 2 ? 11 : 19);
+      for (int i = 0; i < 8; ++i) atomicAdd(o + i, (unsigned long long)st_acc[i]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                        // no CTA of the pair exits while the other may still signal it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+}  // namespace tc
+}  // namespace cube
