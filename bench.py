@@ -36,6 +36,8 @@ WORKLOADS = {
     "hifigan": ("hifigan", 64, 919, "BASELINE configs[2]: batch=64 x 10 s (F=919), HiFi-GAN generator (neb-noft rates [3,5,4,4])"),
     # configs[3]: 256 utterances of 2-15 s on rank 0, LPT-sharded over the ranks, NCCL scatter/gather (strong scaling)
     "ragged": ("hifigan", 256, 0, "BASELINE configs[3]: batch=256 variable-length (2-15 s) utterances, HiFi-GAN generator, sharded across the ranks via NCCL p2p scatter/gather"),
+    # configs[0]: CPU only (the autoregressive ClariNet teacher), timed on a few steady-state samples and extrapolated
+    "teacher_cpu": ("teacher", 1, 173, "BASELINE configs[0]: single 2 s utterance (F=173, T=44288), 80-bin mel, ClariNet teacher (autoregressive) on CPU PyTorch"),
 }
 # algorithmic work per output sample of the dominant kernel (DESIGN.md "Measurement")
 GATE_FLOPS = 2.0 * (2 * 256 * 128 * 3 + 2 * 256 * 80)     # gated dilated conv + conditioning 1x1
@@ -98,10 +100,14 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+HIFIGAN_NEB_CONFIG = {  # data/models/vocoder/neb-noft/config.json: the shipped generator's architecture
+    "resblock": "1", "upsample_rates": [3, 5, 4, 4], "upsample_kernel_sizes": [16, 16, 4, 4], "upsample_initial_channel": 512,
+    "resblock_kernel_sizes": [3, 7, 11], "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5], [1, 3, 5]], "num_mels": 80}
+
+
 def load_weights(arch):
-    """Shipped checkpoints when staged under oracle/_ref/weights, else seeded random weights of the same
-    architecture (throughput does not depend on the values)."""
-    from oracle import clarinet_ref as C, hifigan_ref as H
+    """Shipped checkpoints when staged under oracle/_ref/weights (binary data copied from the reference tree by
+    build()), else seeded random weights of the same architecture (throughput does not depend on the values)."""
     W = os.path.join(ROOT, "oracle", "_ref", "weights")
 
     def ld(n):
@@ -112,21 +118,37 @@ def load_weights(arch):
         s, t = ld("pnn_vocoder.network"), ld("nn_vocoder.network")
         if s is not None and t is not None:
             return (s, t), "shipped pnn_vocoder.network + nn_vocoder.network upsampler"
+        from oracle import clarinet_ref as C      # fallback only: seeded weights with the shipped key layout
         return (C.random_state_dict("student", 1), C.random_state_dict("teacher", 2)), "seeded random-init weights (shipped checkpoints not staged)"
     g = ld("g_00600000")
-    cfg = dict(H.CONFIG_NEB)
+    cfg = dict(HIFIGAN_NEB_CONFIG)
     if g is not None:
         return (g["generator"], cfg), "shipped g_00600000"
+    from oracle import hifigan_ref as H
     return (H.random_state_dict(cfg, seed=1), cfg), "seeded random-init weights (shipped checkpoint not staged)"
 
 
+def synthetic_mel01(B, F, seed, num_mels=80):
+    """SURVEY 8(d) cfg1/cfg2 input: smooth field in [0, 1] (ClariNet-era min/max normalisation)."""
+    g = torch.Generator().manual_seed(seed)
+    r = torch.randn(B, num_mels, F + 8, generator=g)
+    return torch.sigmoid(torch.nn.functional.avg_pool1d(r, 9, stride=1)[:, :, :F] * 3.0).contiguous()
+
+
+def synthetic_logmel(B, F, seed, level=0.0, num_mels=80):
+    """SURVEY 8(d) cfg3 input: natural-log-mel-like smooth field, loud enough that the shipped generator peaks near 0.9."""
+    g = torch.Generator().manual_seed(seed)
+    r = 6.0 * torch.randn(B, num_mels, F + 8, generator=g)
+    sm = torch.nn.functional.avg_pool1d(r, 9, stride=1)[:, :, :F]
+    tilt = torch.linspace(0, 4, num_mels)[None, :, None]
+    return torch.clamp(0.5 * sm - tilt + level, -11.5, 2.5).contiguous()
+
+
 def synth_inputs(arch, B, F, seed):
-    from oracle import clarinet_ref as C, hifigan_ref as H
     if arch == "student":
-        mel = C.synthetic_mel01(B, F, seed=seed)
         z = torch.randn(B, 1, F * 256, generator=torch.Generator().manual_seed(seed + 1))
-        return mel, z
-    return H.synthetic_mel(B, F, seed=seed), None
+        return synthetic_mel01(B, F, seed), z
+    return synthetic_logmel(B, F, seed), None
 
 
 def host_cpus():
@@ -289,12 +311,64 @@ def run_reference(args, arch, B, F, desc, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_teacher_cpu(args, desc, rank):
+    """BASELINE configs[0]: single 2-s utterance, 80-bin mel -> ClariNet TEACHER on CPU PyTorch (no GPU by definition).
+    The teacher is autoregressive: one network evaluation per audio sample.  The reference ships its weights only
+    (data/models/nn_vocoder.network), so the CPU path is the oracle port, whose sampler (oracle/clarinet_ref.py:
+    teacher_generate) recomputes the causal receptive field for every sample.  Timed: `--steps` steady-state samples
+    (full 2 974-sample receptive field each) of the 2-s utterance, extrapolated to its 44 288 samples - stated in `sample`."""
+    if rank != 0:
+        return
+    from oracle import clarinet_ref as C
+    W = os.path.join(ROOT, "oracle", "_ref", "weights", "nn_vocoder.network")
+    if os.path.exists(W):
+        tsd, wdesc = torch.load(W, map_location="cpu", weights_only=False), "shipped nn_vocoder.network"
+    else:
+        tsd, wdesc = C.random_state_dict("teacher", 2), "seeded random-init teacher (checkpoint not staged)"
+    threads = min(host_cpus(), 8)
+    torch.set_num_threads(threads)
+    F, hop = 173, 256
+    T = F * hop
+    nb = C.teacher_blocks_of(tsd)
+    rf = (C.FRONT_K - 1) + sum((C.KERNEL - 1) * C.dilation_of(i) for i in range(nb)) + 1
+    mel = synthetic_mel01(1, F, seed=1234)
+    c_up = C.upsample_mel(tsd, mel)
+    n = max(2, args.steps)
+    start = rf + 64                                       # steady state: the window is the full receptive field
+    g = torch.Generator().manual_seed(7)
+    eps = torch.randn(1, start + n + 1, generator=g)
+    # prime the history with the first `start` samples of a student-like signal (values do not change the cost)
+    x0 = 0.1 * torch.randn(1, 1, start, generator=g)
+    w = {k: v.float() for k, v in C.fold_weight_norm(tsd).items()}
+    x = torch.zeros(1, 1, start + n + 1)
+    x[:, :, :start] = x0
+    for _ in range(max(1, args.warmup)):
+        C.wavenet_forward(w, "", nb, x[:, :, 1:start], c_up[:, :, 1:start])
+    t0 = time.perf_counter()
+    for t in range(start - 1, start - 1 + n):
+        lo = t + 1 - rf
+        ml = C.wavenet_forward(w, "", nb, x[:, :, lo:t + 1], c_up[:, :, lo:t + 1])
+        x[:, 0, t + 1] = ml[:, 0, -1] + 0.8 * eps[:, t] * torch.exp(ml[:, 1, -1])      # cube/networks/loss.py:50-52
+    dt = time.perf_counter() - t0
+    rate = n / dt
+    line = {
+        "impl": "reference", "metric": "audio samples/sec", "value": rate, "unit": "samples/s", "n_gpus": 0, "steps": n, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / n, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic; " + wdesc, "rtf": rate / SR, "config": {"workload": desc, "frames": F, "samples": T, "receptive_field": rf},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} consecutive steady-state samples of the 2-s utterance (each = one teacher evaluation over its {rf}-sample "
+                                   f"receptive field, naive recompute); the whole utterance extrapolates to {T / rate:.0f} s of CPU"},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "utterance_seconds_extrapolated": T / rate, "gpu_launches": 0, "finite": bool(torch.isfinite(x).all()),
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_ragged(args, desc, rank, world, local):
     """configs[3]: rank 0 owns 256 variable-length mels; tts_cube_b200.synthesize shards them (LPT), scatters the
     padded mel blocks, every rank vocodes its shard, rank 0 gathers the audio.  Strong scaling: the work is fixed."""
     import torch.distributed as dist
     import tts_cube_b200 as cube
-    from oracle import hifigan_ref as H
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
@@ -308,13 +382,15 @@ def run_ragged(args, desc, rank, world, local):
     frames = [int(round(float(s_) * SR / 240)) for s_ in secs]
     mels = None
     if rank == 0:
-        big = H.synthetic_mel(1, max(frames) + 64 * 0, seed=77)[0]
+        big = synthetic_logmel(1, max(frames), seed=77)[0]
         mels = [torch.roll(big, shifts=37 * i, dims=1)[:, :f].contiguous().to(dev) for i, f in enumerate(frames)]
     total = sum(voc.out_len(f) for f in frames)
 
+    stats = {}
+
     def step():
         with torch.no_grad():
-            return cube.synthesize(voc, mels, device=dev, max_batch=64, max_frames=64 * 1400)
+            return cube.synthesize(voc, mels, device=dev, max_batch=64, max_frames=64 * 1400, stats=stats)
 
     def barrier():
         if world > 1:
@@ -356,6 +432,10 @@ def run_ragged(args, desc, rank, world, local):
                        "l2": "per-step working set >> 126 MB L2"},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                     "note": "device-resident lists in, device-resident lists out (rank 0); includes padding, scatter, gather"},
+            "collective": {"kind": "NCCL point-to-point only (batch_isend_irecv): rank 0 -> r padded mel blocks, r -> rank 0 audio blocks",
+                           "host_phase_seconds_last_step": {k: v for k, v in stats.items() if k.endswith("_s")},
+                           "scatter_bytes": stats.get("scatter_bytes"), "gather_bytes": stats.get("gather_bytes"),
+                           "batches_per_rank": stats.get("batches_per_rank")},
             "gpu_launches": launches, "clocks": clocks, "lib": cube.build_info()}))
     if world > 1:
         dist.destroy_process_group()
@@ -379,6 +459,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "teacher_cpu":
+        run_teacher_cpu(args, desc, rank)
+        return
     if args.impl == "reference":
         run_reference(args, arch, B, F, desc, rank, world)
         return

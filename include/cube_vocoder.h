@@ -32,6 +32,9 @@ enum cube_voc_arch {
   CUBE_VOC_WAVERNN = 2      /* cube/networks/modules.py:WaveRNN (Path W), autoregressive          */
 };
 
+/* 'beta' (cube/networks/loss.py:69-106, selectable at modules.py:436-437) is NOT supported: its sample() draws from
+ * torch.distributions.Beta (rejection sampling inside torch), which cannot be replayed from injected draws; the Python
+ * layer raises CubeVocError for output='beta' */
 enum cube_wavernn_head { CUBE_HEAD_MOL = 0, CUBE_HEAD_GM = 1, CUBE_HEAD_MULAW = 2, CUBE_HEAD_RAW = 3 };
 
 enum cube_voc_math {
@@ -48,6 +51,9 @@ enum cube_voc_math {
  * (hifigan/models.py:72-98) and, for Path C, the module tree of the shipped checkpoints
  * (SURVEY Appendix C). */
 typedef struct cube_voc_config {
+  uint32_t struct_size; /* = sizeof(cube_voc_config) of the header the caller was built against: cube_voc_create rejects
+                         * any other value, so a binding whose struct has drifted from this header (a missing or extra
+                         * field) fails loudly instead of having the library read past the caller's struct */
   int32_t arch;  /* enum cube_voc_arch */
   int32_t math;  /* enum cube_voc_math */
   int32_t num_mels; /* 80 */
@@ -76,7 +82,8 @@ typedef struct cube_voc_config {
   int32_t wrnn_head;                                  /* enum cube_wavernn_head ('mol','gm','mulaw','raw') */
 } cube_voc_config;
 
-/* Generator(h) / Wavenet_Student(...) constructor.  device = CUDA ordinal. */
+/* Generator(h) / Wavenet_Student(...) constructor.  device = CUDA ordinal.  cfg->struct_size must equal
+ * sizeof(cube_voc_config). */
 int cube_voc_create(cube_voc_t** out, const cube_voc_config* cfg, int device);
 
 /* load_state_dict(): one call per state_dict entry, `name` is the reference's key
@@ -175,6 +182,7 @@ int cube_wav_to_int16(const float* wav, int16_t* out, int64_t n, cube_stream_t s
 typedef struct cube_mel cube_mel_t;
 
 typedef struct cube_mel_config {
+  uint32_t struct_size; /* = sizeof(cube_mel_config); checked by cube_mel_create like cube_voc_config.struct_size */
   int32_t n_fft;      /* 1024; multiple of 4 */
   int32_t win_size;   /* <= n_fft (centred zero padding like torch.stft) */
   int32_t hop_size;   /* 240 / 256; multiple of 4 */
@@ -183,6 +191,8 @@ typedef struct cube_mel_config {
   int32_t pad_right;
   int32_t log10_out;  /* 0: ln (meldataset.py:19-20)   1: log10 (io_utils/vocoder.py:96-98) */
   int32_t layout;     /* 0: [B, n_mels, F] (HiFi-GAN)  1: [B, F, n_mels] (MelVocoder / WaveRNN, time-major) */
+  int32_t pad_mode;   /* 0: reflect (meldataset.py:62; librosa < 0.10 stft default)  1: constant zeros (librosa >= 0.10 stft
+                       * default pad_mode; the reference does not pin librosa, cube/io_utils/vocoder.py:71-73) */
   float mag_eps;      /* sqrt(re^2 + im^2 + eps): 1e-9 in meldataset.py:70, 0 for np.abs */
   float floor_val;    /* clamp before the log: 1e-5 */
   float pad_value;    /* written to frames beyond an utterance's own frame count in a ragged batch */

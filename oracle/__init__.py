@@ -17,5 +17,5 @@ Parity status:
     reference - the forward code is not in the reference tree (weights only);
     ``clarinet_ref`` restates upstream ksw0306/ClariNet (no pinned commit) and is
     anchored by (a) strict key/shape match with the shipped checkpoints and
-    (b) the teacher-NLL self-consistency probe (tests/test_oracle_clarinet.py).
+    (b) the teacher-NLL self-consistency probe (tests/test_oracle.py::test_clarinet_self_consistency_probe).
 """

@@ -13,7 +13,7 @@ restates that published algorithm and anchors it on what the reference does hold
     weights are the teacher's ``upsample_conv.{0,2}`` - pinned bit-for-bit by
     tests/golden/upsample2.npz;
   * the Gaussian head (reference ``cube/networks/loss.py:35-66``);
-  * a self-consistency probe (tests/test_oracle_clarinet.py): student samples must score a far
+  * a self-consistency probe (tests/test_oracle.py::test_clarinet_self_consistency_probe): student samples must score a far
     better teacher NLL under dilation 3^(i mod 6) + sqrt(0.5) residual scaling than under the
     alternatives.
 

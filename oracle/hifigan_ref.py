@@ -6,7 +6,7 @@ Functional fp32 restatement of ``hifigan/models.py:Generator.forward`` (referenc
 own ``state_dict`` (weight-norm ``weight_g``/``weight_v`` pairs or folded ``weight``) so the same
 tensors feed the oracle and the CUDA path.
 
-Pinned: tests/test_oracle_hifigan.py compares this against outputs of the unmodified reference
+Pinned: tests/test_oracle.py::test_hifigan_oracle_matches_reference_* compares this against outputs of the unmodified reference
 module executed in the build container (tests/golden/hifigan_*.npz, made by
 oracle/make_goldens.py); the two agree bit-for-bit on CPU because both end in the same ATen
 conv calls.

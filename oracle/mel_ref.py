@@ -72,7 +72,7 @@ def hifigan_mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_siz
     return torch.log(torch.clamp(torch.matmul(basis, mag), min=1e-5))                   # :72-73, :27-28
 
 
-def cube_melspectrogram(y, sample_rate, num_mels, hop_size, use_preemphasis=False, basis=None):
+def cube_melspectrogram(y, sample_rate, num_mels, hop_size, use_preemphasis=False, basis=None, pad_mode="reflect"):
     """cube/io_utils/vocoder.py:54-62 for ONE utterance y [T] -> [F, num_mels] (log10, time-major):
     optional lfilter([1, -0.97]) (:64-65), librosa.stft(n_fft=1024, hop, win 1024, 'hann') = centred frames of the
     reflect-padded signal (:71-73), |.|, librosa mel basis with fmin=0, fmax=sr/2 (:80-82), log10(max(1e-5, .)) (:96-98)."""
@@ -83,7 +83,7 @@ def cube_melspectrogram(y, sample_rate, num_mels, hop_size, use_preemphasis=Fals
     if basis is None:
         basis = slaney_mel_basis(sample_rate, n_fft, num_mels)
     spec = torch.stft(y[None], n_fft, hop_length=hop_size, win_length=n_fft, window=torch.hann_window(n_fft),
-                      center=True, pad_mode="reflect", return_complex=True)[0]
+                      center=True, pad_mode=pad_mode, return_complex=True)[0]   # librosa < 0.10: reflect; >= 0.10: constant
     mel = torch.matmul(torch.as_tensor(basis), spec.abs())
     return torch.log10(torch.clamp(mel, min=1e-5)).T.contiguous()
 

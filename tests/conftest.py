@@ -15,6 +15,14 @@ WEIGHTS = os.path.join(ROOT, "oracle", "_ref", "weights")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+    config.addinivalue_line("markers", "slow: ~1 min of CPU oracle (full-depth student on a 10 s utterance)")
+    # the CPU oracles are torch fp32 convs: more than a few dozen threads makes them slower, and on a box whose cgroup
+    # quota is below os.cpu_count() a thread per core gets throttled to a crawl
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, min(16, n)))
 
 
 def pytest_collection_modifyitems(config, items):

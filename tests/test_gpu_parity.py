@@ -30,6 +30,35 @@ def _gen(cfg, sd, dev, math=0):
 
 
 
+def _cached_oracle(tag, fn):
+    """CPU oracle results of the long cases are cached on disk (/tmp): the kernel-variant tests re-run this file in
+    child processes (one per env switch) and would otherwise repeat a 45 s CPU run each time."""
+    import hashlib
+    import os
+    d = "/tmp/cube_oracle_cache"
+    os.makedirs(d, exist_ok=True)
+    p = os.path.join(d, hashlib.sha1(tag.encode()).hexdigest()[:16] + ".pt")
+    if os.path.exists(p):
+        try:
+            return torch.load(p)
+        except Exception:
+            pass
+    y = fn()
+    torch.save(y, p + ".tmp")
+    os.replace(p + ".tmp", p)
+    return y
+
+
+def _report(name, y, ref):
+    """max-abs error and where it occurs"""
+    e = (y - ref).abs()
+    k = int(e.argmax())
+    idx = np.unravel_index(k, tuple(e.shape))
+    err = float(e.reshape(-1)[k])
+    print(f"{name}: max-abs {err:.3e} at {tuple(int(i) for i in idx)} of {tuple(e.shape)} (peak {float(ref.abs().max()):.2f}, rms err {float(e.pow(2).mean().sqrt()):.2e})")
+    return err
+
+
 # ------------------------------------------------ Path H ------------------------------------------------
 @pytest.mark.parametrize("name", ["hifigan_mini.npz", "hifigan_mini_rb2.npz"])
 def test_hifigan_golden_mini(dev, name):
@@ -172,6 +201,24 @@ def test_hifigan_full_size_properties(dev, neb, math):
         assert float((y2 - ys).abs().max()) <= 5e-4
 
 
+@pytest.mark.parametrize("math", MATHS)
+@pytest.mark.parametrize("level", [0.0, 1.0])
+def test_hifigan_full_length_oracle(dev, neb, level, math):
+    """BASELINE configs[2] geometry, compared with the oracle over the WHOLE 10-s utterance (F = 919, T = 220 656), the
+    shipped generator, speech level (0) and the saturating corner (+1), both math modes.  hifigan/models.py:100-116."""
+    sd, cfg = neb
+    F = 919
+    mel = H.synthetic_mel(2, F, seed=177 + int(level), level=level)
+    ref = _cached_oracle(f"hifigan_neb_full_F{F}_lvl{level}_seed{177 + int(level)}", lambda: H.generator_forward(sd, cfg, mel))
+    g = _gen(cfg, sd, dev, math)
+    with torch.no_grad():
+        y = g(mel.to(dev)).cpu()
+    assert y.shape == ref.shape == (2, 1, H.out_len(cfg, F))
+    err = _report(f"hifigan 10 s full oracle level={level} math={math}", y, ref)
+    assert float(ref.abs().max()) > 0.5
+    assert err <= TOL
+
+
 # ------------------------------------------------ Path C ------------------------------------------------
 def _student(ssd, tsd, dev, math=0):
     import tts_cube_b200 as cube
@@ -279,6 +326,37 @@ def test_student_full_length_properties(dev, math):
         assert float((a - s_).abs().max()) <= (5e-4 if FP8 else 1e-4)
 
 
+def _student_case(case, F):
+    """inputs of the full-depth parity cases: (mel, z)"""
+    mel = C.synthetic_mel01(1, F, seed=31)
+    z = torch.randn(1, 1, F * 256, generator=torch.Generator().manual_seed(32))
+    if case == "temp0.7":          # the legacy CLI's sampling temperature (examples/tts-colab-demo.ipynb:247)
+        z = z * 0.7
+    elif case == "loud":           # mel pushed towards 1 (ClariNet-era [0,1] normalisation): a loud, dense spectrum
+        mel = mel.sqrt()
+    return mel, z
+
+
+@pytest.mark.parametrize("math", MATHS)
+@pytest.mark.parametrize("case,F", [("plain", 173), ("temp0.7", 173), ("loud", 173),
+                                    pytest.param("plain", 862, marks=pytest.mark.slow)])
+def test_student_shipped_full_depth_oracle(dev, clarinet_weights, case, F, math):
+    """The shipped 42-block student ([6,6,6,24] blocks, 4 IAF flows; receptive field 5 220 samples) against the oracle over
+    WHOLE utterances: F = 173 (BASELINE configs[0] length, 2 s) and F = 862 (configs[1] length, 10 s: ~45 s of CPU oracle,
+    cached on disk for the kernel-variant child processes).  Run for the default kernel (CTA pair + 8-bit correction
+    passes), and through test_variants_in_subprocess for CUBE_TC_FP8=0, the single-CTA kernels and the unfused pair."""
+    ssd, tsd, trained = clarinet_weights
+    mel, z = _student_case(case, F)
+    ref = _cached_oracle(f"student_full_{case}_F{F}_trained{trained}", lambda: C.vocode_student(ssd, tsd, mel, z))
+    v = _student(ssd, tsd, dev, math)
+    with torch.no_grad():
+        x = v(mel.to(dev), z.to(dev)).cpu()
+    assert x.shape == ref.shape == (1, 1, F * 256)
+    err = _report(f"student full depth shipped={trained} case={case} F={F} math={math} fp8={FP8}", x, ref)
+    assert bool(torch.isfinite(x).all()) and float(ref.abs().max()) > 0.1
+    assert err <= TOL
+
+
 # ------------------------------------------------ heads ------------------------------------------------
 def test_mulaw_bit_exact(dev):
     import tts_cube_b200 as cube
@@ -323,6 +401,37 @@ def test_raw_mol_gaussian_categorical(dev):
     # sample() = decode(categorical): values come from the 256-entry table
     s = cube.MULAWOutput().sample(logits.to(dev), u.to(dev)).cpu()
     assert torch.equal(s[ok], W.mulaw_decode(ref)[ok])
+
+
+def test_categorical_distribution(dev):
+    """W2: the Gumbel-max sampler is DISTRIBUTION-equivalent to the reference's `Categorical(logits=y).sample()`
+    (cube/networks/loss.py:227-229, 288-290) - not replayable draw for draw (torch's sampler consumes its generator
+    differently): a chi-square goodness-of-fit of 400 000 draws against softmax(logits), for a peaked and a flat
+    256-way distribution, plus a two-sample check against torch's own Categorical on the CPU."""
+    from scipy import stats
+    from tts_cube_b200.heads import _categorical
+    g = torch.Generator().manual_seed(77)
+    N, Cn = 400_000, 256
+    for scale in (3.0, 0.5):
+        logits = torch.randn(Cn, generator=g) * scale
+        p = torch.softmax(logits.double(), 0).numpy()
+        u = torch.empty(N, Cn).uniform_(1e-5, 1 - 1e-5, generator=g)
+        idx = _categorical(logits.expand(N, Cn).contiguous().to(dev), u.to(dev)).cpu().numpy()
+        cnt = np.bincount(idx, minlength=Cn).astype(np.float64)
+        keep = N * p >= 5                                  # chi-square needs expected counts >= 5: pool the rest
+        obs = np.append(cnt[keep], cnt[~keep].sum())
+        exp = np.append(N * p[keep], N * p[~keep].sum())
+        if exp[-1] < 5:
+            obs, exp = obs[:-1], exp[:-1] * (obs[:-1].sum() / exp[:-1].sum())
+        chi2 = float(((obs - exp) ** 2 / exp).sum())
+        crit = float(stats.chi2.ppf(1 - 1e-6, len(obs) - 1))
+        print(f"categorical chi2 scale={scale}: {chi2:.1f} (df {len(obs) - 1}, critical at p=1e-6: {crit:.1f})")
+        assert chi2 < crit
+        ref = torch.distributions.Categorical(logits=logits).sample((N,)).numpy()    # the reference's sampler, CPU
+        rc = np.bincount(ref, minlength=Cn).astype(np.float64)
+        both = (cnt + rc) >= 10
+        chi2_2 = float((((cnt - rc) ** 2) / (cnt + rc))[both].sum())                   # two-sample chi-square, equal N
+        assert chi2_2 < float(stats.chi2.ppf(1 - 1e-6, int(both.sum()) - 1))
 
 
 # ------------------------------------------------ Path W4 / W5 ------------------------------------------------
@@ -420,6 +529,59 @@ def test_hifigan_tcgen05_edge_cases(dev):
                 assert float(y[0].abs().max()) == 0.0
 
 
+def test_integration_stub_runs_verbatim(dev):
+    """INTEGRATION.md's raw ctypes stub, executed as written, drives the .so to the reference-made golden."""
+    import types
+    from test_host_logic import integration_stub_namespace
+    ns = integration_stub_namespace()
+    d = load_golden("hifigan_mini.npz")
+    cfg = golden_cfg(d)
+    h = types.SimpleNamespace(**cfg)
+    hnd = ns["make_generator"](h, golden_weights(d), device=0)
+    with torch.cuda.device(dev):
+        wav = ns["generate"](hnd, torch.from_numpy(d["mel"]).to(dev))
+        torch.cuda.synchronize()
+    assert float(np.abs(wav.cpu().numpy() - d["wav"]).max()) <= 2e-5
+    ns["lib"].cube_voc_destroy(hnd)
+
+
+# ------------------------------------------------ configs[4]: behind the reference Cubegan ------------------------------------------------
+def test_cubegan_inference_through_the_drop_in(dev):
+    """tests/golden/cubegan_e2e.npz = the unmodified reference `Cubegan.inference` run end to end in the build container
+    (oracle/make_cubegan_golden.py): seeded Languasito2 -> conditioning -> reference Generator.  Here the same
+    conditioning goes through `install_into_cubegan` + the same 8 lines of `inference` and must give the same wav, and
+    the int16 audio of `TTSCube.__call__` (cube/api.py:64-65)."""
+    import types
+    import tts_cube_b200 as cube
+    from test_host_logic import CubeganStandIn, generator_shell
+    d = load_golden("cubegan_e2e.npz")
+    sd = H.random_state_dict(H.CONFIG_V1, seed=int(d["gen_seed"]), std=float(d["gen_std"]), g_scale=float(d["gen_gscale"]))
+    cond = torch.from_numpy(d["conditioning"]).to(dev)                     # [1, F, 80] as Languasito2.inference returns it
+    for math in (None, 0):
+        model = CubeganStandIn(generator_shell(sd, types.SimpleNamespace(**H.CONFIG_V1)).to(dev), [cond])
+        cube.install_into_cubegan(model, math=math)
+        assert isinstance(model._generator, cube.CubeGenerator) and model._generator.device == dev
+        audio = model.inference({"utt": 0})                                # cube/networks/cubegan.py:74-83
+        assert audio.shape == d["wav"].shape
+        err = _report(f"cubegan e2e math={math}", audio.cpu(), torch.from_numpy(d["wav"]))
+        assert err <= TOL
+        a16 = np.asarray(audio.detach().cpu().numpy().squeeze() * 32767, dtype=np.int16)      # cube/api.py:64-65
+        assert np.abs(a16.astype(np.int32) - d["wav_int16"].astype(np.int32)).max() <= int(32767 * err) + 1
+    # batch > 1 glue: several utterances (different lengths) through the per-utterance frontend and ONE batched vocoder call
+    conds = [cond, cond[:, :17].contiguous(), cond[:, :1].contiguous(), cond[:, :0]]
+    model = CubeganStandIn(generator_shell(sd, types.SimpleNamespace(**H.CONFIG_V1)).to(dev), conds)
+    cube.install_into_cubegan(model)
+    wavs = cube.cubegan_inference_batch(model, [{"utt": i} for i in range(4)])
+    w16 = cube.cubegan_inference_batch(model, [{"utt": i} for i in range(4)], int16=True)
+    for i, c in enumerate(conds):
+        if c.shape[1] == 0:                                                # the reference's empty-utterance guard: one zero frame
+            c = torch.zeros(1, 1, 80, device=dev)
+        ref = H.generator_forward(sd, H.CONFIG_V1, c.permute(0, 2, 1).cpu())[0, 0]
+        assert wavs[i].shape == ref.shape and float((wavs[i].cpu() - ref).abs().max()) <= TOL, i
+        assert w16[i].dtype == torch.int16 and torch.equal(w16[i].cpu(), H.wav_to_int16(wavs[i].cpu()))
+    assert float((wavs[0].cpu() - torch.from_numpy(d["wav"])[0, 0]).abs().max()) <= TOL
+
+
 # ------------------------------------------------ mel front-end ------------------------------------------------
 MEL_TOL = 2e-4      # log-mel units (fp32 DFT by direct summation vs torch's FFT; measured ~1e-5)
 
@@ -461,6 +623,11 @@ def test_mel_cube_flavour(dev):
         got = cube.MelVocoder().melspectrogram(y.numpy(), 22050, 80, 256, use_preemphasis=pre, device=dev)
         assert got.shape == ref.shape and got.dtype == np.float32
         assert float(np.abs(got - ref).max()) <= MEL_TOL
+    # librosa >= 0.10 pads stft frames with zeros instead of reflecting (the reference does not pin librosa)
+    ref0 = M.cube_melspectrogram(y, 22050, 80, 256, pad_mode="constant").numpy()
+    got0 = cube.MelVocoder().melspectrogram(y.numpy(), 22050, 80, 256, device=dev, pad_mode="constant")
+    assert got0.shape == ref0.shape and float(np.abs(got0 - ref0).max()) <= MEL_TOL
+    assert float(np.abs(ref0[:2] - ref[:2]).max()) > 1e-2        # the two conventions really differ at the edges
     # 24 kHz / hop 240 (the Cubegan call), too-short input -> error from the library, not garbage
     fe = cube.MelSpectrogram(1024, 80, 24000, 240, 1024, 0, 12000)
     assert fe(torch.zeros(1, 300, device=dev)).shape == (1, 80, 1)       # shorter than the padding: zero frames, one padded row
@@ -488,11 +655,11 @@ def test_mel_copy_synthesis_chain(dev, neb):
 # ------------------------------------------------ kernel variants behind env switches ------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("env,select", [
-    pytest.param({"CUBE_TC_FUSED": "0"}, "student and tcgen05", id="student_unfused_pair"),
+    pytest.param({"CUBE_TC_FUSED": "0"}, "student and tcgen05 and not 862", id="student_unfused_pair"),
     pytest.param({"CUBE_TC_FUSED": "0", "CUBE_TC_CG2": "1"}, "student and tcgen05 and not full_length", id="student_cta_pair"),
     pytest.param({"CUBE_TC_WIN": "0"}, "hifigan and tcgen05 and not full_size and not loudness", id="hifigan_no_window"),
     pytest.param({"CUBE_TC_FP8": "0"}, "student and tcgen05", id="student_pair_fp16x3"),
-    pytest.param({"CUBE_TC_FP8": "0", "CUBE_TC_PAIR": "0"}, "student and tcgen05", id="student_single_cta_fp16x3"),
+    pytest.param({"CUBE_TC_FP8": "0", "CUBE_TC_PAIR": "0"}, "student and tcgen05 and not 862", id="student_single_cta_fp16x3"),
     pytest.param({"CUBE_TC_PAIR": "0"}, "student and tcgen05 and not full_length", id="student_single_cta_fp8"),
 ])
 def test_variants_in_subprocess(env, select):

@@ -27,11 +27,71 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert "sm_100a" in _lib.build_info()
 
 
+def _header_struct_words(name):
+    """count the 4-byte fields of `typedef struct <name> { ... }` in include/cube_vocoder.h (arrays by their extents)"""
+    hdr = open(os.path.join(ROOT, "include", "cube_vocoder.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    consts = {k: int(v) for k, v in re.findall(r"#define\s+(CUBE_MAX_\w+)\s+(\d+)", hdr)}
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, flags=re.S).group(1)
+    n = 0
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        m = re.match(r"(uint32_t|int32_t|float)\s+(.*)", decl, flags=re.S)
+        assert m, decl
+        for var in m.group(2).split(","):
+            k = 1
+            for ext in re.findall(r"\[(\w+)\]", var):
+                k *= consts.get(ext, None) or int(ext)
+            n += k
+    return n
+
+
 def test_config_struct_matches_header_size():
     from tts_cube_b200 import _lib
-    # 3 + 2 + 8 + 8 + 2 + 8 + 8 + 64 + 1 + 8 + 3 + 2 + 2 + 1 + 4 int32 fields
-    assert ctypes.sizeof(_lib.VocConfig) == 4 * (3 + 2 + 16 + 2 + 16 + 64 + 1 + 8 + 3 + 2 + 2 + 1 + 4 + 6)
-    assert ctypes.sizeof(_lib.MelConfig) == 4 * 12      # cube_mel_config: 8 int32 + 4 float
+    assert ctypes.sizeof(_lib.VocConfig) == 4 * _header_struct_words("cube_voc_config")
+    assert ctypes.sizeof(_lib.MelConfig) == 4 * _header_struct_words("cube_mel_config")
+    assert _lib.VocConfig().struct_size == ctypes.sizeof(_lib.VocConfig)
+    assert _lib.MelConfig(n_fft=1024).struct_size == ctypes.sizeof(_lib.MelConfig)
+
+
+def integration_stub_namespace():
+    """exec the raw ctypes stub of INTEGRATION.md verbatim (only the library path is made absolute)"""
+    from tts_cube_b200 import _lib
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"```python\n(# raw-ctypes-stub:.*?)```", md, flags=re.S)
+    assert m, "INTEGRATION.md lost its raw ctypes stub"
+    code = m.group(1)
+    assert 'C.CDLL("libcube_vocoder.so")' in code
+    ns = {}
+    exec(compile(code.replace('"libcube_vocoder.so"', repr(_lib.LIB_PATH)), "INTEGRATION.md:stub", "exec"), ns)
+    return ns
+
+
+def test_integration_stub_matches_the_abi():
+    """the documented stub's struct is the library's struct, and a stale struct (the round-1 stub without the
+    wrnn_* fields) is rejected by struct_size instead of being read out of bounds"""
+    from tts_cube_b200 import _lib
+    ns = integration_stub_namespace()
+    Stub = ns["VocConfig"]
+    assert ctypes.sizeof(Stub) == ctypes.sizeof(_lib.VocConfig)
+    assert [f[0] for f in Stub._fields_] == [f[0] for f in _lib.VocConfig._fields_]
+    lib = ns["lib"]
+    hp = ctypes.c_void_p()
+
+    class Stale(ctypes.Structure):
+        _fields_ = Stub._fields_[:-6]
+    st = Stale(struct_size=ctypes.sizeof(Stale))
+    assert lib.cube_voc_create(ctypes.byref(hp), ctypes.byref(st), 0) != 0
+    assert "struct_size" in ns["last_error"]()
+    zero = Stub()          # struct_size left 0
+    assert lib.cube_voc_create(ctypes.byref(hp), ctypes.byref(zero), 0) != 0
+    assert "struct_size" in ns["last_error"]()
+    if not torch.cuda.is_available():
+        ok = Stub(struct_size=ctypes.sizeof(Stub), n_ups=1, n_resblock_kernels=1, resblock_type=1)
+        assert lib.cube_voc_create(ctypes.byref(hp), ctypes.byref(ok), 0) != 0
+        assert "no CUDA device" in ns["last_error"]()
 
 
 def test_mel_front_end_host_logic():
@@ -104,6 +164,99 @@ def test_make_batches_and_padding():
     assert make_batches(range(6), nf, 64, max_frames=25) == [[0, 1], [2, 3], [4, 5]]
     m = pad_mels([torch.ones(80, 3), torch.ones(80, 5)], pad_value=-5.0)
     assert m.shape == (2, 80, 5) and float(m[0, 0, 4]) == -5.0 and float(m[1, 0, 4]) == 1.0
+
+
+def test_synthesize_draws_noise_for_the_student_when_zs_is_none():
+    """a vocoder that needs z (the IAF student) used to get a 2-argument call when zs=None."""
+    from tts_cube_b200.api import synthesize
+
+    class ParallelWaveNetVocoder:                       # stands in for the CUDA class: same name, same call contract
+        device = torch.device("cpu")
+        calls = []
+
+        def out_len(self, f):
+            return 4 * f
+
+        def __call__(self, mel, z, frames):
+            assert z.shape == (mel.shape[0], 1, 4 * mel.shape[2]) and len(frames) == mel.shape[0]
+            self.calls.append((tuple(mel.shape), float(z.abs().sum())))
+            return mel.mean(1, keepdim=True).repeat_interleave(4, dim=2) + 0 * z
+
+    v = ParallelWaveNetVocoder()
+    mels = [torch.full((80, f), float(f)) for f in (5, 3, 7)]
+    out = synthesize(v, mels, max_batch=2)
+    assert [o.shape[0] for o in out] == [20, 12, 28]
+    assert all(float(o[0]) == f for o, f in zip(out, (5, 3, 7)))
+    assert all(zsum > 0 for _, zsum in v.calls)          # noise was drawn, not zeros
+    zs = [torch.zeros(4 * f) for f in (5, 3, 7)]
+    v.calls.clear()
+    synthesize(v, mels, zs=zs, max_batch=2)
+    assert all(zsum == 0 for _, zsum in v.calls)         # injected z is what reaches the vocoder
+
+
+def generator_shell(sd, h):
+    """A parameter tree with the reference Generator's state_dict keys and `.h` - what install_into_cubegan reads of
+    `model._generator` (cube/networks/cubegan.py:41-43) - without importing the reference."""
+    root = torch.nn.Module()
+    root.h = h
+    for key, val in sd.items():
+        mod = root
+        parts = key.split(".")
+        for part in parts[:-1]:
+            if not hasattr(mod, part):
+                mod.add_module(part, torch.nn.Module())
+            mod = getattr(mod, part)
+        mod.register_parameter(parts[-1], torch.nn.Parameter(val.clone(), requires_grad=False))
+    return root
+
+
+class CubeganStandIn(torch.nn.Module):
+    """The attributes and the 8 lines of `Cubegan.inference` (cube/networks/cubegan.py:74-83) that the drop-in touches;
+    the frontend returns a stored conditioning (made by the real Languasito2 in oracle/make_cubegan_golden.py)."""
+
+    class _Frontend(torch.nn.Module):
+        def __init__(self, conds):
+            super().__init__()
+            self.conds = conds
+
+        def inference(self, X, hf_cond=None):
+            return self.conds[int(X["utt"])]
+
+    def __init__(self, generator, conds):
+        super().__init__()
+        self._generator = generator
+        self._languasito = CubeganStandIn._Frontend(conds)
+        self._hf = None
+
+    def get_device(self):
+        return next(self._generator.parameters()).device if list(self._generator.parameters()) else self._generator.device
+
+    def inference(self, X):
+        with torch.no_grad():
+            hf_cond = None
+            conditioning = self._languasito.inference(X, hf_cond=hf_cond)
+            if conditioning.shape[1] == 0:
+                conditioning = torch.zeros((conditioning.shape[0], 1, conditioning.shape[2]), device=self.get_device())
+            return self._generator(conditioning.permute(0, 2, 1))
+
+
+def test_install_into_cubegan_swaps_the_generator():
+    import types
+    import tts_cube_b200 as cube
+    from oracle import hifigan_ref as H
+    cfg = dict(H.CONFIG_V1, upsample_initial_channel=32)
+    sd = H.random_state_dict(cfg, seed=11)
+    model = CubeganStandIn(generator_shell(sd, types.SimpleNamespace(**cfg)), [])
+    cube.install_into_cubegan(model)
+    g = model._generator
+    assert isinstance(g, cube.CubeGenerator) and g.device.type == "cpu"
+    assert set(g.state_dict()) == set(sd) and all(torch.equal(g.state_dict()[k], sd[k]) for k in sd)
+    assert g._cfg.upsample_initial_channel == 32 and g._cfg.math == 0      # auto: stage widths 16..2 -> the fp32 kernels
+    from tts_cube_b200.generator import hifigan_config
+    assert hifigan_config(H.CONFIG_V1).math == 1                           # config_v1 (what Cubegan hard-codes): tensor cores
+    if not torch.cuda.is_available():
+        with pytest.raises(cube.CubeVocError):                             # still no CPU path behind the reference call
+            g(torch.zeros(1, 80, 4))
 
 
 def _free_port():

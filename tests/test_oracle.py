@@ -166,3 +166,20 @@ def test_mel_cube_flavour_properties():
     yp = y.clone()
     yp[1:] = y[1:] - 0.97 * y[:-1]
     assert torch.allclose(M.cube_melspectrogram(y, 22050, 80, 256, use_preemphasis=True), M.cube_melspectrogram(yp, 22050, 80, 256))
+
+
+def test_teacher_generate_is_consistent_with_teacher_forcing():
+    """configs[0] path of the oracle: autoregressive sampling (truncated-window recompute) reproduces itself under
+    teacher forcing - x[t+1] = mean_t + 0.8 eps_t exp(log_std_t) with (mean, log_std) from ONE causal pass over the
+    finished waveform (cube/networks/loss.py:50-52 for the head)."""
+    tsd = C.random_state_dict("teacher", 6, blocks=[3])
+    mel = C.synthetic_mel01(1, 1, seed=3)
+    c_up = C.upsample_mel(tsd, mel)[:, :, :96]
+    eps = torch.randn(1, 96, generator=torch.Generator().manual_seed(2))
+    x = C.teacher_generate(tsd, c_up, eps)
+    assert x.shape == (1, 1, 96) and float(x[0, 0, 0]) == 0.0 and bool(torch.isfinite(x).all())
+    w = {k: v.float() for k, v in C.fold_weight_norm(tsd).items()}
+    ml = C.wavenet_forward(w, "", 3, x, c_up)
+    want = ml[:, 0, :-1] + 0.8 * eps[:, :-1] * torch.exp(ml[:, 1, :-1])
+    assert float((x[:, 0, 1:] - want).abs().max()) <= 1e-5
+    assert float(x.abs().max()) > 1e-3

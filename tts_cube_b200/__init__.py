@@ -14,7 +14,7 @@ from .generator import CubeGenerator, install_into_cubegan  # noqa: F401
 from .clarinet import ParallelWaveNetVocoder  # noqa: F401
 from .heads import MULAWOutput, RAWOutput, MOLOutput, GaussianOutput  # noqa: F401
 from .wavernn import WaveRNNVocoder, CubenetVocoder  # noqa: F401
-from .api import synthesize, lpt_shard  # noqa: F401
+from .api import synthesize, lpt_shard, cubegan_inference_batch  # noqa: F401
 from .mel import MelSpectrogram, MelVocoder, mel_spectrogram, slaney_mel_basis  # noqa: F401
 
 __version__ = "0.1.0"

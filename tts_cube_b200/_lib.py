@@ -1,8 +1,7 @@
 """ctypes binding of libcube_vocoder.so (C ABI: include/cube_vocoder.h).
 
 There is deliberately no fallback: if the shared library is missing or cannot be loaded, importing
-any compute entry point raises.  The library is built in-tree by ``__graft_entry__.build()`` /
-``python -m tts_cube_b200.build``.
+any compute entry point raises.  The library is built in-tree by ``__graft_entry__.build()``.
 """
 from __future__ import annotations
 
@@ -19,7 +18,9 @@ MATH_FP32_SIMT, MATH_TC_SPLIT16 = 0, 1
 
 
 class VocConfig(C.Structure):
+    """cube_voc_config; ``struct_size`` is filled in by the constructor (the library rejects a mismatch)."""
     _fields_ = [
+        ("struct_size", C.c_uint32),
         ("arch", C.c_int32), ("math", C.c_int32), ("num_mels", C.c_int32),
         ("upsample_initial_channel", C.c_int32), ("n_ups", C.c_int32),
         ("upsample_rates", C.c_int32 * MAX_UPS), ("upsample_kernel_sizes", C.c_int32 * MAX_UPS),
@@ -35,11 +36,21 @@ class VocConfig(C.Structure):
         ("wrnn_upsample_low", C.c_int32), ("wrnn_use_lowres", C.c_int32), ("wrnn_head", C.c_int32),
     ]
 
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.struct_size = C.sizeof(VocConfig)
+
 
 class MelConfig(C.Structure):
-    _fields_ = [("n_fft", C.c_int32), ("win_size", C.c_int32), ("hop_size", C.c_int32), ("n_mels", C.c_int32),
+    _fields_ = [("struct_size", C.c_uint32),
+                ("n_fft", C.c_int32), ("win_size", C.c_int32), ("hop_size", C.c_int32), ("n_mels", C.c_int32),
                 ("pad_left", C.c_int32), ("pad_right", C.c_int32), ("log10_out", C.c_int32), ("layout", C.c_int32),
+                ("pad_mode", C.c_int32),
                 ("mag_eps", C.c_float), ("floor_val", C.c_float), ("pad_value", C.c_float), ("preemph", C.c_float)]
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.struct_size = C.sizeof(MelConfig)
 
 
 class CubeVocError(RuntimeError):

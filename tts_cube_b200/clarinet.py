@@ -63,6 +63,10 @@ class ParallelWaveNetVocoder(torch.nn.Module):
         self.register_buffer("_device_tracker", torch.zeros(1), persistent=False)
 
     @property
+    def device(self) -> torch.device:
+        return self._device_tracker.device
+
+    @property
     def hop(self) -> int:
         h = 1
         for i in range(self._cfg.n_upsample):

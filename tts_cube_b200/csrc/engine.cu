@@ -1201,7 +1201,9 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
   const int R = c.res_channels, G = c.gate_channels, S = c.skip_channels, CI = c.num_mels, K = c.kernel_size;
   if (upload_lens(h, n_frames, B, Fmax, c.n_upsample + 1, st)) return 1;
   const int* lens_T = h->d_lens + (size_t)c.n_upsample * B;
-  float *cmid, *cup, *hb, *ob, *sk, *y1, *za, *zb;
+  float *cmid, *cmid2 = nullptr, *cup, *hb, *ob, *sk, *y1, *za, *zb;
+  // intermediate stages of the upsampler ping-pong between two buffers (a stage never reads and writes the same one)
+  if (c.n_upsample > 2 && ws_get(h, "c_mid2", (size_t)B * CI * (T / c.upsample_scales[c.n_upsample - 1] + 1), &cmid2)) return 1;
   if (ws_get(h, "c_up", (size_t)B * CI * T, &cup) || ws_get(h, "c_mid", (size_t)B * CI * (T / c.upsample_scales[c.n_upsample - 1] + 1), &cmid) ||
       ws_get(h, "h", c.math == CUBE_MATH_TC_SPLIT16 ? 16 : (size_t)B * R * T, &hb) ||
       ws_get(h, "o", c.math == CUBE_MATH_TC_SPLIT16 ? 16 : (size_t)B * G * T, &ob) ||
@@ -1217,7 +1219,7 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
       Up2dP p;
       memset(&p, 0, sizeof(p));
       const int s = h->up2[n].s;
-      p.src = src; p.out = (n == c.n_upsample - 1) ? cup : cmid;
+      p.src = src; p.out = (n == c.n_upsample - 1) ? cup : ((n & 1) ? cmid2 : cmid);
       p.src_lens = h->d_lens; p.lens_scale = scale;
       p.nf = CI; p.L_in = Lin; p.L_out = Lin * s; p.s = s; p.pad = s / 2;
       memcpy(p.w, h->up2[n].w, sizeof(p.w));
@@ -1703,6 +1705,9 @@ const char* cube_voc_build_info(void) {
 
 int cube_voc_create(cube_voc_t** out, const cube_voc_config* cfg, int device) {
   if (!out || !cfg) return fail("null argument");
+  if (cfg->struct_size != sizeof(cube_voc_config))
+    return fail("cube_voc_config.struct_size = %u but this library's struct is %zu bytes: the binding does not match include/cube_vocoder.h",
+                cfg->struct_size, sizeof(cube_voc_config));
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -1992,6 +1997,9 @@ struct cube_mel {
 int cube_mel_create(cube_mel_t** out, const cube_mel_config* cfg, const float* window, const float* mel_basis, int device) {
   using namespace cube;
   if (!out || !cfg || !mel_basis) return fail("null argument");
+  if (cfg->struct_size != sizeof(cube_mel_config))
+    return fail("cube_mel_config.struct_size = %u but this library's struct is %zu bytes: the binding does not match include/cube_vocoder.h",
+                cfg->struct_size, sizeof(cube_mel_config));
   const cube_mel_config& c = *cfg;
   if (c.n_fft < 16 || c.n_fft > 4096 || c.n_fft % 4) return fail("n_fft must be a multiple of 4 in [16, 4096] (got %d)", c.n_fft);
   if (c.hop_size < 4 || c.hop_size % 4) return fail("hop_size must be a positive multiple of 4 (got %d)", c.hop_size);
@@ -1999,6 +2007,7 @@ int cube_mel_create(cube_mel_t** out, const cube_mel_config* cfg, const float* w
   if (c.n_mels < 1 || c.n_mels > 512) return fail("n_mels out of range (%d)", c.n_mels);
   if (c.pad_left < 0 || c.pad_right < 0) return fail("negative padding");
   if (c.layout != 0 && c.layout != 1) return fail("layout must be 0 ([B,M,F]) or 1 ([B,F,M])");
+  if (c.pad_mode != 0 && c.pad_mode != 1) return fail("pad_mode must be 0 (reflect) or 1 (constant zeros)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("no CUDA device: libcube_vocoder has no CPU fallback");
   if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
@@ -2046,7 +2055,7 @@ int cube_mel_create(cube_mel_t** out, const cube_mel_config* cfg, const float* w
 
 int64_t cube_mel_out_frames(const cube_mel_t* h, int64_t n_samples) {
   if (!h || n_samples < 0 || n_samples > INT32_MAX) return -1;
-  return cube::mel::n_frames_of((int)n_samples, h->cfg.n_fft, h->cfg.hop_size, h->cfg.pad_left, h->cfg.pad_right);
+  return cube::mel::n_frames_of((int)n_samples, h->cfg.n_fft, h->cfg.hop_size, h->cfg.pad_left, h->cfg.pad_right, h->cfg.pad_mode);
 }
 
 int cube_mel_forward(cube_mel_t* h, const float* wav, const int32_t* n_samples, float* out, int B, int64_t Tmax, int64_t Fmax,
@@ -2076,7 +2085,7 @@ int cube_mel_forward(cube_mel_t* h, const float* wav, const int32_t* n_samples, 
   p.cosT = h->cosT; p.sinT = h->sinT; p.basis = h->basis; p.k_lo = h->k_lo; p.k_hi = h->k_hi; p.out = out;
   p.B = B; p.Tmax = (int)Tmax; p.Fmax = (int)Fmax;
   p.n_fft = h->cfg.n_fft; p.hop = h->cfg.hop_size; p.n_bins = h->n_bins; p.KB = h->KB; p.n_mels = h->cfg.n_mels;
-  p.pad_left = h->cfg.pad_left; p.pad_right = h->cfg.pad_right; p.layout = h->cfg.layout; p.log10_out = h->cfg.log10_out;
+  p.pad_left = h->cfg.pad_left; p.pad_right = h->cfg.pad_right; p.layout = h->cfg.layout; p.log10_out = h->cfg.log10_out; p.pad_mode = h->cfg.pad_mode;
   p.mag_eps = h->cfg.mag_eps; p.floor_val = h->cfg.floor_val; p.pad_value = h->cfg.pad_value; p.preemph = h->cfg.preemph;
   {  // the opt-in shared-memory limit is per kernel and device, not per handle: only ever raise it
     static size_t granted[64] = {0};

@@ -33,13 +33,14 @@ struct MelParams {
   int B, Tmax, Fmax;
   int n_fft, hop, n_bins, KB, n_mels;
   int pad_left, pad_right;
-  int layout, log10_out;
+  int layout, log10_out, pad_mode;   // pad_mode 0: reflect at the utterance's own ends, 1: zeros
   float mag_eps, floor_val, pad_value, preemph;
 };
 
 // frames an utterance of L samples yields (torch.stft on the reflect-padded signal; reflect needs pad < L)
-__host__ __device__ inline int n_frames_of(int L, int n_fft, int hop, int pl, int pr) {
-  if (L <= pl || L <= pr || L + pl + pr < n_fft) return 0;
+__host__ __device__ inline int n_frames_of(int L, int n_fft, int hop, int pl, int pr, int pad_mode = 0) {
+  if (pad_mode == 0 && (L <= pl || L <= pr)) return 0;
+  if (L < 1 || L + pl + pr < n_fft) return 0;
   return 1 + (L + pl + pr - n_fft) / hop;
 }
 
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(THREADS) melspec_kernel(const MelParams p) {
   float* mag = smem + span4;                // [FT][mpitch]
   const int b = blockIdx.y, f0 = blockIdx.x * FT;
   const int L = p.n_samples ? min(p.n_samples[b], p.Tmax) : p.Tmax;
-  const int Fb = n_frames_of(L, p.n_fft, p.hop, p.pad_left, p.pad_right);
+  const int Fb = n_frames_of(L, p.n_fft, p.hop, p.pad_left, p.pad_right, p.pad_mode);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (f0 < Fb) {
@@ -61,8 +62,10 @@ __global__ void __launch_bounds__(THREADS) melspec_kernel(const MelParams p) {
     const int g0 = f0 * p.hop - p.pad_left;
     for (int i = threadIdx.x; i < span4; i += THREADS) {
       int g = g0 + i;
-      if (g < 0) g = -g;
-      if (g >= L) g = 2 * (L - 1) - g;
+      if (p.pad_mode == 0) {
+        if (g < 0) g = -g;
+        if (g >= L) g = 2 * (L - 1) - g;
+      }
       float v = 0.f;
       if (i < span && g >= 0 && g < L) {
         v = x[g];

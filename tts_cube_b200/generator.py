@@ -33,6 +33,7 @@ class _Handle:
     def __init__(self, cfg: VocConfig, device: torch.device):
         self.ptr = C.c_void_p()
         self.device = device
+        self.num_mels = int(cfg.num_mels)
         check(lib().cube_voc_create(C.byref(self.ptr), C.byref(cfg), device.index or 0))
 
     def load(self, sd: Mapping[str, torch.Tensor]) -> None:
@@ -56,6 +57,9 @@ class _Handle:
             raise _lib.CubeVocError("mel must live on a CUDA device (no CPU path)")
         if mel.dtype != torch.float32 or mel.dim() != 3:
             raise _lib.CubeVocError(f"mel must be float32 [B, C, F], got {mel.dtype} {tuple(mel.shape)}")
+        self._check_shapes(mel, n_frames)
+        if mel.device != self.device:
+            raise _lib.CubeVocError(f"mel lives on {mel.device} but this vocoder's weights live on {self.device}")
         mel = mel.contiguous()
         B, _, F = mel.shape
         T = self.out_len(F)
@@ -75,9 +79,35 @@ class _Handle:
                 B, F, C.c_void_p(_stream_ptr(mel.device))))
         return (wav, w16) if want_int16 else wav
 
+    def _check_shapes(self, mel: torch.Tensor, n_frames) -> None:
+        """The engine trusts num_mels and B: a narrower tensor or a short n_frames list would be read out of bounds."""
+        if mel.shape[1] != self.num_mels:
+            raise _lib.CubeVocError(f"mel has {mel.shape[1]} channels, this vocoder was built for num_mels={self.num_mels}")
+        if mel.shape[0] < 1 or mel.shape[2] < 1:
+            raise _lib.CubeVocError(f"empty batch {tuple(mel.shape)}")
+        if n_frames is not None and len(n_frames) != mel.shape[0]:
+            raise _lib.CubeVocError(f"n_frames has {len(n_frames)} entries for a batch of {mel.shape[0]}")
+
     def forward_host(self, mel: torch.Tensor, n_frames, noise: Optional[torch.Tensor], out: torch.Tensor):
         """Host buffers in, host buffer out (H2D + forward + D2H inside the library)."""
+        if mel.dim() != 3:
+            raise _lib.CubeVocError(f"mel must be [B, C, F], got {tuple(mel.shape)}")
+        for name, t in (("mel", mel), ("noise", noise), ("out", out)):
+            if t is None:
+                continue
+            if t.device.type != "cpu" or not t.is_contiguous():
+                raise _lib.CubeVocError(f"forward_host takes contiguous HOST tensors; `{name}` is {t.device}, contiguous={t.is_contiguous()}")
+        if mel.dtype != torch.float32 or (noise is not None and noise.dtype != torch.float32):
+            raise _lib.CubeVocError("forward_host takes float32 mel / noise")
+        if out.dtype not in (torch.float32, torch.int16):
+            raise _lib.CubeVocError(f"`out` must be float32 or int16, got {out.dtype}")
+        self._check_shapes(mel, n_frames)
         B, _, F = mel.shape
+        T = self.out_len(F)
+        if out.numel() != B * T:
+            raise _lib.CubeVocError(f"`out` must hold B*T = {B}*{T} samples, got {tuple(out.shape)}")
+        if noise is not None and noise.numel() != B * T:
+            raise _lib.CubeVocError(f"noise must have B*T = {B * T} elements, got {noise.numel()}")
         nf = (C.c_int32 * B)(*[int(v) for v in n_frames]) if n_frames is not None else None
         wav_p = C.c_void_p(out.data_ptr()) if out.dtype == torch.float32 else None
         i16_p = C.c_void_p(out.data_ptr()) if out.dtype == torch.int16 else None

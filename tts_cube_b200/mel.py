@@ -69,9 +69,14 @@ class MelSpectrogram:
     [B, F, num_mels] (time-major, what WaveRNN / the ClariNet-era tools consume)."""
 
     def __init__(self, n_fft=1024, num_mels=80, sampling_rate=22050, hop_size=256, win_size=1024, fmin=0.0, fmax=None,
-                 flavor="hifigan", preemphasis=0.0, pad_value=None, device=None, mel_basis=None):
+                 flavor="hifigan", preemphasis=0.0, pad_value=None, device=None, mel_basis=None, pad_mode="reflect"):
         if flavor not in ("hifigan", "cube"):
             raise ValueError("flavor must be 'hifigan' or 'cube'")
+        if pad_mode not in ("reflect", "constant"):
+            # the reference calls librosa.stft with library defaults and does not pin librosa: < 0.10 pads with
+            # 'reflect', >= 0.10 with 'constant' zeros (first / last ~2 frames differ); hifigan/meldataset.py:62 is
+            # always 'reflect'
+            raise ValueError("pad_mode must be 'reflect' or 'constant'")
         self.n_fft, self.num_mels, self.hop_size, self.flavor = int(n_fft), int(num_mels), int(hop_size), flavor
         hif = flavor == "hifigan"
         pad = (self.n_fft - self.hop_size) // 2 if hif else self.n_fft // 2
@@ -80,6 +85,7 @@ class MelSpectrogram:
             pad_value = float(np.log(floor)) if hif else -5.0
         self.cfg = _lib.MelConfig(n_fft=self.n_fft, win_size=int(win_size), hop_size=self.hop_size, n_mels=self.num_mels,
                                   pad_left=pad, pad_right=pad, log10_out=0 if hif else 1, layout=0 if hif else 1,
+                                  pad_mode=0 if pad_mode == "reflect" else 1,
                                   mag_eps=1e-9 if hif else 0.0, floor_val=floor, pad_value=float(pad_value),
                                   preemph=float(preemphasis))
         self.basis = slaney_mel_basis(sampling_rate, n_fft, num_mels, fmin, fmax) if mel_basis is None else np.asarray(mel_basis)
@@ -90,7 +96,7 @@ class MelSpectrogram:
 
     def n_frames(self, n_samples: int) -> int:
         c = self.cfg
-        if n_samples <= c.pad_left or n_samples + c.pad_left + c.pad_right < c.n_fft:
+        if (c.pad_mode == 0 and n_samples <= c.pad_left) or n_samples < 1 or n_samples + c.pad_left + c.pad_right < c.n_fft:
             return 0
         return 1 + (n_samples + c.pad_left + c.pad_right - c.n_fft) // c.hop_size
 
@@ -136,11 +142,11 @@ def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin,
 class MelVocoder:
     """``cube/io_utils/vocoder.py:MelVocoder`` (the melspectrogram part) with the STFT on the GPU."""
 
-    def melspectrogram(self, y, sample_rate, num_mels, hop_size, use_preemphasis=False, device="cuda"):
+    def melspectrogram(self, y, sample_rate, num_mels, hop_size, use_preemphasis=False, device="cuda", pad_mode="reflect"):
         """y: 1-D numpy array or tensor -> numpy float32 [F, num_mels] (log10 mel, floor 1e-5), like the reference."""
-        key = ("cube", sample_rate, num_mels, hop_size, bool(use_preemphasis), str(device))
+        key = ("cube", sample_rate, num_mels, hop_size, bool(use_preemphasis), str(device), pad_mode)
         if key not in _CACHE:
             _CACHE[key] = MelSpectrogram(1024, num_mels, sample_rate, hop_size, 1024, 0.0, None, flavor="cube",
-                                         preemphasis=0.97 if use_preemphasis else 0.0)
+                                         preemphasis=0.97 if use_preemphasis else 0.0, pad_mode=pad_mode)
         t = torch.as_tensor(np.asarray(y, dtype=np.float32) if not torch.is_tensor(y) else y, dtype=torch.float32).to(device)
         return _CACHE[key](t).cpu().numpy()

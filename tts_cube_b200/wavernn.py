@@ -27,7 +27,10 @@ class WaveRNNVocoder(torch.nn.Module):
         super().__init__()
         lib()
         if output not in _lib.HEADS:
-            raise _lib.CubeVocError(f"output '{output}' is not supported on the GPU path (mol, gm, mulaw, raw)")
+            raise _lib.CubeVocError(
+                f"output '{output}' is not supported on the GPU path (mol, gm, mulaw, raw).  'beta' (reference cube/networks/loss.py:69-106) "
+                "samples through torch.distributions.Beta, whose internal gamma rejection sampler cannot be replayed from injected draws; "
+                "no shipped model uses it")
         self._output = output
         self._upsample, self._upsample_low, self._use_lowres = int(upsample), int(upsample_low), bool(use_lowres)
         cfg = VocConfig()
@@ -51,6 +54,10 @@ class WaveRNNVocoder(torch.nn.Module):
 
     def state_dict(self, *a, **k):
         return dict(self._sd)
+
+    @property
+    def device(self) -> torch.device:
+        return self._device_tracker.device
 
     def _apply(self, fn, *a, **k):
         before = self._device_tracker.device
