@@ -232,10 +232,21 @@ def cpu_sample_shape(rate, F, hop, seconds):
     return batch, frames
 
 
-def cpu_probe_rate(arch, weights, threads):
-    """samples/s on a clip long enough to be representative (conv efficiency grows with length) yet ~1 s of CPU"""
-    r, _, _ = cpu_oracle_rate(arch, weights, 24 if arch == "student" else 400, threads)
-    return r
+def cpu_calibrated_sample(arch, weights, threads, F, hop, seconds, max_rounds=3):
+    """(batch, frames, samples/s) of a CPU sample that takes about `seconds`.  The rate of torch's CPU convs depends on
+    the clip length (short clips live in cache, long ones stream from DRAM), so a short probe is only a first guess:
+    the sample is re-sized from its OWN measured rate until it lands within [0.6, 1.5] x the budget, growing by at
+    most 4x per round - no round can overshoot the budget by more than the rate drop between two sizes."""
+    rate, _, _ = cpu_oracle_rate(arch, weights, 12 if arch == "student" else 200, threads)      # ~0.5 s probe
+    target = min(seconds, 1.0)
+    cb, frames = cpu_sample_shape(rate, F, hop, target)
+    for _ in range(max_rounds):
+        rate, n, dt = cpu_oracle_rate(arch, weights, frames, threads, cb)
+        if 0.6 * seconds <= dt <= 1.5 * seconds:
+            break
+        target = min(seconds, 4.0 * dt) if dt < seconds else seconds
+        cb, frames = cpu_sample_shape(rate, F, hop, target)
+    return cb, frames, rate
 
 
 def torch_cuda_baseline(arch, weights, mel, z, steps=2):
@@ -284,11 +295,10 @@ def run_reference(args, arch, B, F, desc, rank, world):
     t_start = time.perf_counter()
     weights, wdesc = load_weights(arch)
     threads = best_cpu_threads(arch, weights)
-    rate = cpu_probe_rate(arch, weights, threads)
     n_calls = max(1, args.steps + args.warmup)
-    budget = min(6.0, 90.0 / n_calls)                                   # seconds of CPU per step
+    budget = min(5.0, 75.0 / n_calls)                                   # seconds of CPU per step
     hop = 256 if arch == "student" else 240
-    cb, frames = cpu_sample_shape(0.8 * rate, F, hop, budget)
+    cb, frames, _ = cpu_calibrated_sample(arch, weights, threads, F, hop, budget)
     for _ in range(args.warmup):
         cpu_oracle_rate(arch, weights, frames, threads, cb)
     tot_s, tot_t = 0, 0.0
@@ -609,9 +619,8 @@ def main():
             tgpu = torch_cuda_baseline(arch, weights, sets[0][0], sets[0][1])
     if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only (the N>1 lines carry null)
         threads = best_cpu_threads(arch, weights)     # cached in /tmp by the reference arm when that ran first
-        rate = cpu_probe_rate(arch, weights, threads)
         hop = 256 if arch == "student" else 240
-        cb, frames = cpu_sample_shape(0.8 * rate, F, hop, 12.0)
+        cb, frames, _ = cpu_calibrated_sample(arch, weights, threads, F, hop, 10.0)
         r2, n, dt = cpu_oracle_rate(arch, weights, frames, threads, cb)
         cpu = {"value": r2, "unit": "samples/s", "cores": threads, "kind": "port",
                "sample": f"B={cb} x {frames} frames ({n} samples, {dt:.1f} s of CPU) of the same synthetic workload; oracle port, torch CPU fp32, "

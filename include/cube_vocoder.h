@@ -167,7 +167,10 @@ int cube_mol_sample(const float* y, const float* u_mix, const float* u_x, float*
 /* GaussianOutput.sample (loss.py:50-52) with injected normals: y [N,2], eps [N] -> x [N] */
 int cube_gaussian_sample(const float* y, const float* eps, float* x, int64_t n, cube_stream_t stream);
 /* Categorical(logits).sample() for MULAW/RAW (loss.py:227-229, 288-290) in Gumbel-max form with
- * injected uniforms: logits [N, C], u [N, C] -> idx [N] int64 */
+ * injected uniforms: logits [N, C], u [N, C] in [0, 1) -> idx [N] int64 = argmax(logits - log(-log u)).
+ * DISTRIBUTION-equivalent to the reference's sampler (chi-square tested against softmax(logits) and against
+ * torch's Categorical), not replayable draw for draw: torch consumes its generator differently.  Feed full-range
+ * uniforms - a truncated range such as (1e-5, 1 - 1e-5) caps the Gumbel noise and starves the rare classes. */
 int cube_categorical_sample(const float* logits, const float* u, int64_t* idx, int64_t n, int C,
                             cube_stream_t stream);
 /* cube/api.py:65: int16(audio * 32767), truncation toward zero */

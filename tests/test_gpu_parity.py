@@ -415,7 +415,7 @@ def test_categorical_distribution(dev):
     for scale in (3.0, 0.5):
         logits = torch.randn(Cn, generator=g) * scale
         p = torch.softmax(logits.double(), 0).numpy()
-        u = torch.empty(N, Cn).uniform_(1e-5, 1 - 1e-5, generator=g)
+        u = torch.rand(N, Cn, generator=g)            # full-range uniforms (a truncated range biases the rare classes)
         idx = _categorical(logits.expand(N, Cn).contiguous().to(dev), u.to(dev)).cpu().numpy()
         cnt = np.bincount(idx, minlength=Cn).astype(np.float64)
         keep = N * p >= 5                                  # chi-square needs expected counts >= 5: pool the rest
@@ -432,6 +432,14 @@ def test_categorical_distribution(dev):
         both = (cnt + rc) >= 10
         chi2_2 = float((((cnt - rc) ** 2) / (cnt + rc))[both].sum())                   # two-sample chi-square, equal N
         assert chi2_2 < float(stats.chi2.ppf(1 - 1e-6, int(both.sum()) - 1))
+    # the default draws of the Python layer (no `u` given) are distribution-correct too
+    logits = torch.randn(Cn, generator=g) * 3.0
+    p = torch.softmax(logits.double(), 0).numpy()
+    idx = _categorical(logits.expand(N, Cn).contiguous().to(dev)).cpu().numpy()
+    cnt = np.bincount(idx, minlength=Cn).astype(np.float64)
+    keep = N * p >= 5
+    chi2 = float(((cnt[keep] - N * p[keep]) ** 2 / (N * p[keep])).sum())
+    assert chi2 < float(stats.chi2.ppf(1 - 1e-6, int(keep.sum())))
 
 
 # ------------------------------------------------ Path W4 / W5 ------------------------------------------------
@@ -658,6 +666,7 @@ def test_mel_copy_synthesis_chain(dev, neb):
     pytest.param({"CUBE_TC_FUSED": "0"}, "student and tcgen05 and not 862", id="student_unfused_pair"),
     pytest.param({"CUBE_TC_FUSED": "0", "CUBE_TC_CG2": "1"}, "student and tcgen05 and not full_length", id="student_cta_pair"),
     pytest.param({"CUBE_TC_WIN": "0"}, "hifigan and tcgen05 and not full_size and not loudness", id="hifigan_no_window"),
+    pytest.param({"CUBE_TC_RBFUSE": "0"}, "hifigan and tcgen05 and not loudness", id="hifigan_unfused_resblock_steps"),
     pytest.param({"CUBE_TC_FP8": "0"}, "student and tcgen05", id="student_pair_fp16x3"),
     pytest.param({"CUBE_TC_FP8": "0", "CUBE_TC_PAIR": "0"}, "student and tcgen05 and not 862", id="student_single_cta_fp16x3"),
     pytest.param({"CUBE_TC_PAIR": "0"}, "student and tcgen05 and not full_length", id="student_single_cta_fp8"),

@@ -19,6 +19,7 @@
 #include "tc_conv.cuh"
 #include "tc_block.cuh"
 #include "tc_block_pair.cuh"
+#include "tc_rbstep.cuh"
 #include "wavernn.cuh"
 #include "melspec.cuh"
 
@@ -972,6 +973,30 @@ static bool use_cg2() {
   return v == 1;
 }
 
+// fused ResBlock-step kernel (tc_rbstep.cuh) for the 32- and 64-channel HiFi-GAN stages: CUBE_TC_RBFUSE=0 falls back to
+// the conv1 / conv2 pair of tc_conv_kernel launches
+static bool use_rbstep() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CUBE_TC_RBFUSE"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+template <int C, int NSUB>
+static int launch_rbstep(cube_voc* h, tc::RbParams& rp, cudaStream_t st) {
+  using Cfg = tc::RbCfg<C, NSUB>;
+  static bool attr[64] = {false};
+  if (!attr[h->device & 63]) {
+    CU_TRY(cudaFuncSetAttribute(tc::tc_rbstep_kernel<C, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr[h->device & 63] = true;
+  }
+  const int r_out = NSUB * tc::BM - (rp.k - 1);
+  rp.t_tiles = (rp.L + r_out - 1) / r_out;
+  const long long tiles = (long long)rp.t_tiles * rp.B;
+  const int grid = (int)std::min<long long>(tiles, h->sm_count);
+  tc::tc_rbstep_kernel<C, NSUB><<<grid, tc::NUM_THREADS, Cfg::SMEM, st>>>(rp);
+  return 0;
+}
+
 // tp.T = rows per batch item; fills t_tiles for the chosen variant and launches
 template <int TN>
 static void launch_tc_t(cube_voc* h, tc::TcParams& tp, cudaStream_t st) {
@@ -1128,7 +1153,39 @@ static int forward_hifigan_tc(cube_voc* h, const float* mel, const int32_t* n_fr
       const int idx = i * nk + j, k = c.resblock_kernel_sizes[j], nd = c.n_dilations[j];
       const int accm = (nk == 1) ? tc::TC_ACC_ADD_DIV : (j == 0 ? tc::TC_ACC_SET : (j == nk - 1 ? tc::TC_ACC_ADD_DIV : tc::TC_ACC_ADD));
       const __half* xcur = U;
-      for (int m = 0; m < nd; ++m) {
+      // narrow stages: the whole step (conv1 -> lrelu -> conv2 -> + x) in one launch, a1 never leaves the SM.  The step
+      // reads x through halo windows of OTHER tiles, so it cannot run in place: outputs ping-pong between R and T1.
+      const bool fuse_rb = use_rbstep() && (ch == 32 || ch == 64) && k >= 1 && k <= 17 && (k & 1);
+      for (int m = 0; m < nd && fuse_rb; ++m) {
+        const int d = c.resblock_dilations[j][m];
+        if (d * (k - 1) > tc::BM) return fail("fused ResBlock step: dilation %d x kernel %d exceeds the staged window", d, k);
+        lx.begin("rb_fused");
+        tc::RbParams rp;
+        memset(&rp, 0, sizeof(rp));
+        if (make_tmap_hl16(&rp.tmX, xcur, B, Lo, ch)) return 1;
+        const TcPacked &w1 = h->tc_c1[idx][m], &w2 = h->tc_c2[idx][m];
+        rp.W1 = w1.Wimg; rp.inv1 = w1.inv_scale; rp.bias1 = w1.bias;
+        rp.W2 = w2.Wimg; rp.inv2 = w2.inv_scale; rp.bias2 = w2.bias;
+        rp.k = k; rp.dil = d; rp.B = B; rp.L = Lo; rp.lens = lens_out;
+        rp.x16 = xcur; rp.slope = LR; rp.inv_slope = 1.f / LR;
+        const bool last = (m == nd - 1);
+        __half* outp = (m & 1) ? T1 : R;
+        if (!last) {
+          rp.out16 = outp;
+        } else {
+          rp.acc32 = xs; rp.acc_mode = accm; rp.acc_div = (float)nk;
+          if (accm == tc::TC_ACC_ADD_DIV) {
+            rp.acc_store = last_stage ? 1 : 0;
+            rp.out16b = last_stage ? nullptr : NX;
+          }
+        }
+        if (ch == 32) { if (launch_rbstep<32, 4>(h, rp, st)) return 1; }
+        else { if (launch_rbstep<64, 2>(h, rp, st)) return 1; }
+        lx.check();
+        lx.end();
+        xcur = outp;
+      }
+      for (int m = 0; m < nd && !fuse_rb; ++m) {
         const int d = c.resblock_dilations[j][m];
         {
           lx.begin("rb_conv1");
@@ -1375,8 +1432,10 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
         if (pairv == 1) {
           static bool attrp[64] = {false};
           if (!attrp[h->device & 63]) {
-            CU_TRY(cudaFuncSetAttribute(tc::tc_block_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PAIR_SMEM));
-            CU_TRY(cudaFuncSetAttribute(tc::tc_block_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PAIR_SMEM));
+            CU_TRY(cudaFuncSetAttribute(tc::tc_block_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PAIR_SMEM));
+            CU_TRY(cudaFuncSetAttribute(tc::tc_block_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PAIR_SMEM));
+            CU_TRY(cudaFuncSetAttribute(tc::tc_block_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PAIR_SMEM));
+            CU_TRY(cudaFuncSetAttribute(tc::tc_block_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PAIR_SMEM));
             attrp[h->device & 63] = true;
           }
           bp.t_tiles = (T + 2 * tc::BM - 1) / (2 * tc::BM);               // a pair's tile is 256 rows
@@ -1391,8 +1450,15 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
           at[0].id = cudaLaunchAttributeClusterDimension;
           at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
           cfg.attrs = at; cfg.numAttrs = 1;
-          if (q8) CU_TRY(cudaLaunchKernelEx(&cfg, tc::tc_block_pair_kernel<true>, bp));
-          else CU_TRY(cudaLaunchKernelEx(&cfg, tc::tc_block_pair_kernel<false>, bp));
+          static int direct = -1;     // both CTAs' loads complete on the leader's barrier (no relay thread); CUBE_PAIR_DIRECT=0: relay
+          if (direct < 0) { const char* e = getenv("CUBE_PAIR_DIRECT"); direct = (e && e[0] == '1') ? 1 : 0; }
+          if (direct) {
+            if (q8) CU_TRY(cudaLaunchKernelEx(&cfg, tc::tc_block_pair_kernel<true, true>, bp));
+            else CU_TRY(cudaLaunchKernelEx(&cfg, tc::tc_block_pair_kernel<false, true>, bp));
+          } else {
+            if (q8) CU_TRY(cudaLaunchKernelEx(&cfg, tc::tc_block_pair_kernel<true, false>, bp));
+            else CU_TRY(cudaLaunchKernelEx(&cfg, tc::tc_block_pair_kernel<false, false>, bp));
+          }
         } else
         if (block_stats_on()) {   // instrumented build: wait cycles of CTA 0 per barrier, printed by block_stats_dump()
           bp.stats = block_stats_buf();

@@ -32,7 +32,10 @@ __device__ __forceinline__ void pair_arrive(uint64_t* bar, uint32_t crank) {
   if (crank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0);
 }
 
-template <bool Q8>
+// DIRECT: the TMA / bulk loads of BOTH CTAs complete on the LEADER's stage barrier (a shared::cluster address), which the
+// leader arms with the bytes of both stages; the relay thread of the peer (wait own barrier -> remote arrive on the
+// leader's `pfull`) and its polling + DSMEM hop per stage disappear.  (CUBE_PAIR_DIRECT=0 selects the relay protocol.)
+template <bool Q8, bool DIRECT = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_pair_kernel(const __grid_constant__ BlockParams p) {
   constexpr bool STATS = false;                    // (the instrumented build exists for the 1-CTA kernel only)
   long long st_acc[1] = {0};
@@ -109,24 +112,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_pair_kernel(const __g
               const int st = it % NST;
               BLK_WAIT(&empty[st], ((it / NST) & 1) ^ 1, 0);
               uint8_t* sb = smem + st * STG;
-              mbar_expect_tx(&full[st], STG);
+              const uint32_t fbar = DIRECT ? mapa_u32(smem_u32(&full[st]), 0) : smem_u32(&full[st]);
+              if (!DIRECT) mbar_expect_tx(&full[st], STG);
+              else if (crank == 0) mbar_expect_tx(&full[st], 2 * STG);
               const CUtensorMap* tm = cond ? &p.tmC : &p.tmH;
-              tma_load_3d(sb, tm, &full[st], cc * BK, row, b);
+              tma_load_3d_bar(sb, tm, fbar, cc * BK, row, b);
               if constexpr (Q8) {
                 // a_hi fp16 (8 KB) | e4m3(a_hi) (4 KB) | e5m2(16 a_lo) (4 KB); one 32 KB weight image
                 const CUtensorMap* tm8 = cond ? &p.tmC8 : &p.tmH8;
-                tma_load_3d(sb + A_TILE_BYTES, tm8, &full[st], cc * BK, row, b);
-                tma_load_3d(sb + A_TILE_BYTES + A_TILE_BYTES / 2, tm8, &full[st], cc * BK, row, p.B + b);
+                tma_load_3d_bar(sb + A_TILE_BYTES, tm8, fbar, cc * BK, row, b);
+                tma_load_3d_bar(sb + A_TILE_BYTES + A_TILE_BYTES / 2, tm8, fbar, cc * BK, row, p.B + b);
                 // rows [128 crank, +128) of each of the three sub-images of the 32 KB chunk image
                 const uint8_t* wq = p.W1q + ((size_t)nt * nch1 + chunk) * 32768;
-                bulk_load(sb + 2 * A_TILE_BYTES, wq + crank * B_BYTES, B_BYTES, &full[st]);
-                bulk_load(sb + 2 * A_TILE_BYTES + B_BYTES, wq + 16384 + crank * (B_BYTES / 2), B_BYTES / 2, &full[st]);
-                bulk_load(sb + 2 * A_TILE_BYTES + B_BYTES + B_BYTES / 2, wq + 24576 + crank * (B_BYTES / 2), B_BYTES / 2, &full[st]);
+                bulk_load_bar(sb + 2 * A_TILE_BYTES, wq + crank * B_BYTES, B_BYTES, fbar);
+                bulk_load_bar(sb + 2 * A_TILE_BYTES + B_BYTES, wq + 16384 + crank * (B_BYTES / 2), B_BYTES / 2, fbar);
+                bulk_load_bar(sb + 2 * A_TILE_BYTES + B_BYTES + B_BYTES / 2, wq + 24576 + crank * (B_BYTES / 2), B_BYTES / 2, fbar);
               } else {
-                tma_load_3d(sb + A_TILE_BYTES, tm, &full[st], cc * BK, row, p.B + b);
+                tma_load_3d_bar(sb + A_TILE_BYTES, tm, fbar, cc * BK, row, p.B + b);
                 const __half* wc = wt + (size_t)chunk * 2 * (BN * BK) + (size_t)crank * (BN / 2) * BK;   // this CTA's 128 weight rows
-                bulk_load(sb + 2 * A_TILE_BYTES, wc, B_BYTES, &full[st]);
-                bulk_load(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, &full[st]);
+                bulk_load_bar(sb + 2 * A_TILE_BYTES, wc, B_BYTES, fbar);
+                bulk_load_bar(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, fbar);
               }
             }
           }
@@ -135,10 +140,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_pair_kernel(const __g
           const int st = it % NST;
           BLK_WAIT(&empty[st], ((it / NST) & 1) ^ 1, 1);
           uint8_t* sb = smem + st * STG;
-          mbar_expect_tx(&full[st], 2 * B_BYTES);
+          const uint32_t fbar = DIRECT ? mapa_u32(smem_u32(&full[st]), 0) : smem_u32(&full[st]);
+          if (!DIRECT) mbar_expect_tx(&full[st], 2 * B_BYTES);
+          else if (crank == 0) mbar_expect_tx(&full[st], 4 * B_BYTES);
           const __half* wc = p.W2 + (size_t)ch * 2 * (BN * BK) + (size_t)crank * (BN / 2) * BK;
-          bulk_load(sb + 2 * A_TILE_BYTES, wc, B_BYTES, &full[st]);
-          bulk_load(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, &full[st]);
+          bulk_load_bar(sb + 2 * A_TILE_BYTES, wc, B_BYTES, fbar);
+          bulk_load_bar(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, fbar);
         }
       }
       if (STATS && p.stats && blockIdx.x == 0) {
@@ -149,7 +156,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_pair_kernel(const __g
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0 && crank != 0) {
+    if (lane == 0 && crank != 0 && DIRECT) {
+      // peer CTA, direct protocol: its loads complete on the leader's barriers; nothing to do here
+    } else if (lane == 0 && crank != 0) {
       // peer CTA: it issues no MMA; this thread relays "my stage has landed" to the leader
       uint32_t it = 0;
       for (int tile = blockIdx.x >> 1; tile < total_tiles; tile += gridDim.x >> 1)
@@ -179,7 +188,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_pair_kernel(const __g
             for (int cc = 0; cc < ncc; ++cc, ++it) {
               const int st = it % NST;
               BLK_WAIT(&full[st], (it / NST) & 1, 2);
-              mbar_wait(&pfull[st], (it / NST) & 1);
+              if (!DIRECT) mbar_wait(&pfull[st], (it / NST) & 1);
               tc_fence_after();
               const uint32_t a_hi = smem_u32(smem + st * STG), a_lo = a_hi + A_TILE_BYTES;
               const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + B_BYTES;
@@ -222,7 +231,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_pair_kernel(const __g
             for (int c4 = 0; c4 < 4; ++c4, ++it) {
               const int st = it % NST;
               BLK_WAIT(&full[st], (it / NST) & 1, 6);
-              mbar_wait(&pfull[st], (it / NST) & 1);
+              if (!DIRECT) mbar_wait(&pfull[st], (it / NST) & 1);
               tc_fence_after();
               const uint32_t a_hi = smem_u32(o_smem + c4 * 2 * A_TILE_BYTES), a_lo = a_hi + A_TILE_BYTES;
               const uint32_t b_hi = smem_u32(smem + st * STG) + 2 * A_TILE_BYTES, b_lo = b_hi + B_BYTES;

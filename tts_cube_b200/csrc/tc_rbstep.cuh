@@ -1,0 +1,378 @@
+// One HiFi-GAN ResBlock1 step in ONE tcgen05 kernel (sm_100a), for the narrow stages (C = 32, 64 channels):
+//     y1 = conv1_{k, dil}(lrelu(x)) + b1                  GEMM1, K = k * C          (hifigan/models.py:37-39)
+//     a1 = lrelu(y1)                                       stays ON CHIP (TMEM -> registers -> swizzled smem A tiles)
+//     y2 = conv2_{k, 1}(a1) + b2                           GEMM2, K = k * C          (hifigan/models.py:40-41)
+//     x' = y2 + x                                          (:42)
+// The unfused pair (two tc_conv_kernel launches) round-trips a1 through HBM as 4-byte hi/lo planes and re-reads x as the
+// residual: 5 plane passes per step where the algorithm needs 2 (read x, write x').  These stages are HBM-bound on the
+// tensor cores (24-176 FLOP/B), so the passes are the time.  Here a CTA stages ONE window of x per tile
+// (rows [t0 - h2 - h1, ...), h1 = dil (k-1)/2, h2 = (k-1)/2), runs conv1 on NSUB*128 rows (the h2 halo rows of a1 that conv2
+// needs are recomputed: 2 h2 of NSUB*128 rows, 2-4 %), writes a1 as K-major SWIZZLE_64B tiles into shared memory, and
+// conv2's taps read them through row-offset descriptors (window mode of tc_conv.cuh).  Tile = NSUB*128 - 2 h2 output rows.
+//
+// Every A-operand tensor holds leaky-ReLU'd values (slope 0.1) as split-fp16 (hi, lo) planes, channels-last
+// [2][B][L][C], exactly as tc_conv_kernel's TC_EPI_CONV leaves them; arithmetic is the same error-compensated
+// a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with fp32 accumulation in TMEM.
+//
+// Roles (576 threads, as tc_conv_kernel): warp 0 = TMA producer (x window, weight ring), warp 1 = MMA issuer,
+// warps 2-17 = epilogue.  Software pipeline over the tiles of a CTA (it = tile counter):
+//     producer :  X(it)  W1(it)  W2(it-1)
+//     MMA      :  M1(it)         M2(it-1)          (conv1 of the next tile is issued BEFORE conv2 of this one, so the
+//     epilogue :  E1(it)         E2(it-1)           tensor pipe runs M1(it) while E1(it-1)'s a1 tiles are being written)
+// TMEM: two buffers of [acc1: NSUB*C | acc2: NSUB*C] columns = 512.
+#pragma once
+#include "tc_conv.cuh"
+
+namespace cube {
+namespace tc {
+
+template <int C, int NSUB> struct RbCfg {
+  static_assert(C == 32 || C == 64, "narrow stages only");
+  static constexpr int NCH = C / BK;                               // K chunks (of 32 channels) per tap
+  static_assert(NSUB * NCH == 4, "16 epilogue warps = 4 lane quarters x (NSUB sub-tiles x NCH column chunks)");
+  static constexpr int NBOX = NSUB + 1;                            // 128-row boxes of the x window (2 h1 <= 128)
+  static constexpr int XPLANE = NBOX * A_TILE_BYTES;               // one (chunk, plane) of the window
+  static constexpr int XWIN = NCH * 2 * XPLANE;
+  static constexpr int MPLANE = NSUB * A_TILE_BYTES;               // one (chunk, plane) of a1
+  static constexpr int MID = NCH * 2 * MPLANE + 1024;              // + slack: the last tap of the last sub-tile reads 2 h2 rows past the end
+  static constexpr int WIMG = 2 * C * BK * 2;                      // (hi, lo) image of one (tap, chunk): C rows x 32 ch
+  static constexpr int WS_ = (222 * 1024 - XWIN - MID - 1024) / WIMG;
+  static constexpr int WS = WS_ > 12 ? 12 : WS_;                   // weight ring depth
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM = 1024 + XWIN + MID + WS * WIMG + BAR_BYTES + 2 * C * 8;
+  static constexpr int ACC = NSUB * C;                             // columns of one accumulator
+  static_assert(4 * ACC == 512, "TMEM budget");
+  static_assert(WS >= 4, "weight ring too shallow");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+struct RbParams {
+  CUtensorMap tmX;            // input planes lrelu(x): fp16 [2B][L][C] channels-last, box {32 ch, 128 rows, 1}, SWIZZLE_64B
+  const __half* W1;           // conv1 images [k taps][NCH][2 planes][C x 32] (pack_tc_conv1d)
+  const __half* W2;           // conv2 images, same layout
+  const float* inv1; const float* bias1;   // [C] power-of-two de-scale and bias of conv1
+  const float* inv2; const float* bias2;
+  int k, dil;                 // conv1: k taps at dilation dil; conv2: k taps at dilation 1; "same" padding
+  int B, L, t_tiles;          // L rows per batch item; t_tiles = ceil(L / (NSUB*128 - (k-1)))
+  const int* lens;            // [B] valid rows (rows >= len are written as zero) or null
+  const __half* x16;          // the same input planes, for the residual (x = inverse leaky-ReLU of the stored value)
+  float slope, inv_slope;     // 0.1, 10
+  __half* out16;              // lrelu(x') planes [2][B][L][C] (next step's input), or null on a ResBlock's last step
+  // last step of a ResBlock: the stage's running sum, fp32 [B][C][L] channel-first (TC_ACC_* of tc_conv.cuh)
+  float* acc32; int acc_mode; float acc_div; int acc_store;
+  __half* out16b;             // TC_ACC_ADD_DIV: lrelu((acc + x') / acc_div) planes = the next stage's input
+};
+
+template <int C, int NSUB>
+__global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_constant__ RbParams p) {
+  using Cfg = RbCfg<C, NSUB>;
+  constexpr int NCH = Cfg::NCH, NBOX = Cfg::NBOX, WS = Cfg::WS, ACC = Cfg::ACC;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* xwin = smem;                                   // [NCH][hi, lo][NBOX boxes]
+  uint8_t* mid = xwin + Cfg::XWIN;                        // [NCH][hi, lo][NSUB tiles] (+ slack)
+  uint8_t* wring = mid + Cfg::MID;                        // [WS][hi image | lo image]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wring + WS * Cfg::WIMG);
+  uint64_t* xfull = bars;                // [1]
+  uint64_t* xempty = bars + 1;           // [1]
+  uint64_t* wfull = bars + 2;            // [WS]
+  uint64_t* wempty = wfull + WS;         // [WS]
+  uint64_t* a1full = wempty + WS;        // [2]  MMA -> epilogue
+  uint64_t* a1free = a1full + 2;         // [2]  epilogue (16 warps) -> MMA
+  uint64_t* a2full = a1free + 2;         // [2]
+  uint64_t* a2free = a2full + 2;         // [2]
+  uint64_t* midfull = a2free + 2;        // [1]  epilogue (16 warps) -> MMA
+  uint64_t* midfree = midfull + 1;       // [1]  MMA -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(midfree + 1);
+  static_assert((2 + 2 * WS + 10) * 8 + 8 <= Cfg::BAR_BYTES, "barrier block");
+  float2* sb1 = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);   // [C] (de-scale, bias) of conv1
+  float2* sb2 = sb1 + C;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h2 = (p.k - 1) / 2, h1 = p.dil * h2;
+  const int R_OUT = NSUB * BM - 2 * h2;                   // output rows of a tile
+  const int total_tiles = p.t_tiles * p.B;
+  int my_tiles = 0;
+  if ((int)blockIdx.x < total_tiles) my_tiles = (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmX);
+    mbar_init(xfull, 1); mbar_init(xempty, 1);
+    for (int s = 0; s < WS; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&a1full[a], 1); mbar_init(&a1free[a], NUM_EPI_WARPS);
+      mbar_init(&a2full[a], 1); mbar_init(&a2free[a], NUM_EPI_WARPS);
+    }
+    mbar_init(midfull, NUM_EPI_WARPS); mbar_init(midfree, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < C; i += NUM_THREADS) {
+    sb1[i] = make_float2(__ldg(p.inv1 + i), __ldg(p.bias1 + i));
+    sb2[i] = make_float2(__ldg(p.inv2 + i), __ldg(p.bias2 + i));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t iw = 0;
+      int x_next = 0;                                         // next tile whose x window has not been requested yet
+      // the x window of tile x_next may be loaded as soon as conv1 of tile x_next-1 has read the buffer; that moment falls
+      // in the middle of this thread's weight streaming (which is paced by the MMAs), so every wait polls for it
+      auto try_x = [&](bool block) {
+        if (x_next >= my_tiles) return;
+        const uint32_t par = (x_next & 1) ^ 1;
+        if (block) mbar_wait(xempty, par);
+        else if (!mbar_try_wait(xempty, par)) return;
+        const int tile = (int)blockIdx.x + x_next * (int)gridDim.x;
+        const int tt = tile % p.t_tiles, b = tile / p.t_tiles;
+        const int r0 = tt * R_OUT - h2 - h1;                 // first row of the x window
+        mbar_expect_tx(xfull, Cfg::XWIN);
+        for (int cc = 0; cc < NCH; ++cc)
+          for (int bx = 0; bx < NBOX; ++bx) {
+            tma_load_3d(xwin + (cc * 2 + 0) * Cfg::XPLANE + bx * A_TILE_BYTES, &p.tmX, xfull, cc * BK, r0 + bx * BM, b);
+            tma_load_3d(xwin + (cc * 2 + 1) * Cfg::XPLANE + bx * A_TILE_BYTES, &p.tmX, xfull, cc * BK, r0 + bx * BM, p.B + b);
+          }
+        ++x_next;
+      };
+      auto weights = [&](const __half* W) {                 // the k * NCH images of one conv, in the MMA thread's order
+        for (int img = 0; img < p.k * NCH; ++img, ++iw) {
+          const int s = iw % WS;
+          while (!mbar_try_wait(&wempty[s], ((iw / WS) & 1) ^ 1)) try_x(false);
+          mbar_expect_tx(&wfull[s], Cfg::WIMG);
+          bulk_load(wring + s * Cfg::WIMG, W + (size_t)img * (Cfg::WIMG / 2), Cfg::WIMG, &wfull[s]);
+        }
+      };
+      for (int it = 0; it <= my_tiles; ++it) {
+        if (it < my_tiles) {
+          if (x_next <= it) try_x(true);                      // X(it), unless it went out early
+          weights(p.W1);
+        }
+        if (it > 0) weights(p.W2);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(C, BM);
+      uint32_t iw = 0;
+      // one conv over the NSUB sub-tiles: A planes at a_base (+ cc*2*plane_bytes), tap j starts `tap_rows * j` rows in
+      auto conv = [&](uint32_t d_tmem, uint32_t a_base, uint32_t plane_bytes, int tap_rows) {
+        uint32_t accumulate = 0;
+        for (int tap = 0; tap < p.k; ++tap)
+          for (int cc = 0; cc < NCH; ++cc, ++iw) {
+            const int s = iw % WS;
+            mbar_wait(&wfull[s], (iw / WS) & 1);
+            tc_fence_after();
+            const uint32_t b_hi = smem_u32(wring + s * Cfg::WIMG), b_lo = b_hi + Cfg::WIMG / 2;
+            const uint32_t a_hi0 = a_base + (uint32_t)(cc * 2) * plane_bytes + (uint32_t)(tap * tap_rows) * ROW_BYTES;
+            const uint32_t a_lo0 = a_hi0 + plane_bytes;
+#pragma unroll
+            for (int ks = 0; ks < BK / 16; ++ks) {
+              const uint32_t ko = ks * 32;
+#pragma unroll
+              for (int ms = 0; ms < NSUB; ++ms) {
+                const uint32_t a_hi = a_hi0 + ms * A_TILE_BYTES + ko, a_lo = a_lo0 + ms * A_TILE_BYTES + ko;
+                const uint32_t d = d_tmem + ms * C;
+                umma_f16(d, make_desc(a_hi), make_desc(b_hi + ko), idesc, accumulate);
+                umma_f16(d, make_desc(a_hi), make_desc(b_lo + ko), idesc, 1);
+                umma_f16(d, make_desc(a_lo), make_desc(b_hi + ko), idesc, 1);
+              }
+              accumulate = 1;
+            }
+            umma_commit(&wempty[s]);
+          }
+      };
+      for (int it = 0; it <= my_tiles; ++it) {
+        if (it < my_tiles) {                                   // M1(it): conv1 of tile it
+          const uint32_t buf = it & 1, ph = (it >> 1) & 1;
+          mbar_wait(&a1free[buf], ph ^ 1);
+          mbar_wait(xfull, it & 1);
+          tc_fence_after();
+          conv(tmem_base + buf * 2 * ACC, smem_u32(xwin), Cfg::XPLANE, p.dil);
+          umma_commit(xempty);
+          umma_commit(&a1full[buf]);
+        }
+        if (it > 0) {                                          // M2(it-1): conv2 of the previous tile
+          const int jt = it - 1;
+          const uint32_t buf = jt & 1, ph = (jt >> 1) & 1;
+          mbar_wait(&a2free[buf], ph ^ 1);
+          mbar_wait(midfull, jt & 1);
+          tc_fence_after();
+          conv(tmem_base + buf * 2 * ACC + ACC, smem_u32(mid), Cfg::MPLANE, 1);
+          umma_commit(midfree);
+          umma_commit(&a2full[buf]);
+        }
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 2..17) ===========================
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int grp = (warp - 2) >> 2;        // 0..3
+    const int ms = grp % NSUB;              // 128-row sub-tile
+    const int cc = grp / NSUB;              // 32-column chunk
+    const int row = q * 32 + lane;          // row inside the sub-tile
+    const int m = ms * BM + row;            // row inside the tile's NSUB*128 rows
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    for (int it = 0; it <= my_tiles; ++it) {
+      if (it < my_tiles) {
+        // ---------------- E1(it): a1 = lrelu(conv1 + b1) -> shared-memory A tiles of conv2 ----------------
+        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const int tt = tile % p.t_tiles, b = tile / p.t_tiles;
+        const int t = tt * R_OUT - h2 + m;                     // time step of this a1 row
+        const int len = p.lens ? min(p.lens[b], p.L) : p.L;
+        const bool valid = t >= 0 && t < len;                  // outside the utterance a1 is the conv's ZERO padding
+        const uint32_t buf = it & 1, ph = (it >> 1) & 1;
+        mbar_wait(&a1full[buf], ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + buf * 2 * ACC + ms * C + cc * 32 + lane_addr;
+        uint32_t hi2[16], lo2[16];
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          uint32_t r[16];
+          tmem_ld16(taddr + ci * 16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float2 s0 = sb1[cc * 32 + ci * 16 + j], s1 = sb1[cc * 32 + ci * 16 + j + 1];
+            float v0 = fmaf(__uint_as_float(r[j]), s0.x, s0.y), v1 = fmaf(__uint_as_float(r[j + 1]), s1.x, s1.y);
+            v0 = v0 < 0.f ? v0 * p.slope : v0;
+            v1 = v1 < 0.f ? v1 * p.slope : v1;
+            split16x2(valid ? v0 : 0.f, valid ? v1 : 0.f, hi2[ci * 8 + (j >> 1)], lo2[ci * 8 + (j >> 1)]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a1free[buf]);              // accumulator drained
+        mbar_wait(midfree, (it & 1) ^ 1);                      // conv2 of the previous tile has read the a1 tiles
+        // K-major SWIZZLE_64B tile [128 rows][32 ch]: 16-byte piece c16 of row r lives at piece c16 ^ ((r >> 1) & 3)
+        uint8_t* mt = mid + (cc * 2) * Cfg::MPLANE + ms * A_TILE_BYTES;
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+          const uint32_t off = row * 64 + ((c16 ^ ((row >> 1) & 3)) << 4);
+          *reinterpret_cast<uint4*>(mt + off) = make_uint4(hi2[4 * c16], hi2[4 * c16 + 1], hi2[4 * c16 + 2], hi2[4 * c16 + 3]);
+          *reinterpret_cast<uint4*>(mt + Cfg::MPLANE + off) = make_uint4(lo2[4 * c16], lo2[4 * c16 + 1], lo2[4 * c16 + 2], lo2[4 * c16 + 3]);
+        }
+        fence_proxy_async();                                   // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(midfull);
+      }
+      if (it > 0) {
+        // ---------------- E2(it-1): x' = conv2 + b2 + x -> global ----------------
+        const int jt = it - 1;
+        const int tile = (int)blockIdx.x + jt * (int)gridDim.x;
+        const int tt = tile % p.t_tiles, b = tile / p.t_tiles;
+        const int t = tt * R_OUT + m;
+        const int len = p.lens ? min(p.lens[b], p.L) : p.L;
+        const bool o_in = m < R_OUT && t < p.L;                // rows this tile owns
+        const bool o_valid = o_in && t < len;
+        const size_t rowoff = ((size_t)b * p.L + (o_in ? t : 0)) * C + cc * 32;
+        const size_t plane = (size_t)p.B * p.L * C;
+        if (o_in) {                                            // residual rows: in L2 since the window load of this tile
+          prefetch_l2(p.x16 + rowoff);
+          prefetch_l2(p.x16 + plane + rowoff);
+        }
+        const uint32_t buf = jt & 1, ph = (jt >> 1) & 1;
+        mbar_wait(&a2full[buf], ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + buf * 2 * ACC + ACC + ms * C + cc * 32 + lane_addr;
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c0 = ci * 16;
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          uint32_t rh[8], rl[8];
+          float old[16];
+          if (o_in) {
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              const uint4 a = reinterpret_cast<const uint4*>(p.x16 + rowoff + c0)[v];
+              const uint4 c = reinterpret_cast<const uint4*>(p.x16 + plane + rowoff + c0)[v];
+              rh[4 * v] = a.x; rh[4 * v + 1] = a.y; rh[4 * v + 2] = a.z; rh[4 * v + 3] = a.w;
+              rl[4 * v] = c.x; rl[4 * v + 1] = c.y; rl[4 * v + 2] = c.z; rl[4 * v + 3] = c.w;
+            }
+          } else {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) rh[v] = rl[v] = 0u;
+          }
+          if (p.acc32 && p.acc_mode >= TC_ACC_ADD && o_in) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) old[j] = __ldcs(p.acc32 + ((size_t)b * C + cc * 32 + c0 + j) * p.L + t);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) old[j] = 0.f;
+          }
+          tmem_ld_wait();
+          if (ci == 1) {                                       // last TMEM read of this warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a2free[buf]);
+          }
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float2 s0 = sb2[cc * 32 + c0 + j], s1 = sb2[cc * 32 + c0 + j + 1];
+            const float2 ah = unpack_h2(rh[j >> 1]), al = unpack_h2(rl[j >> 1]);
+            float a0 = ah.x + al.x, a1 = ah.y + al.y;          // stored lrelu(x): invert
+            a0 = a0 < 0.f ? a0 * p.inv_slope : a0;
+            a1 = a1 < 0.f ? a1 * p.inv_slope : a1;
+            v[j] = o_valid ? fmaf(__uint_as_float(r[j]), s0.x, s0.y) + a0 : 0.f;
+            v[j + 1] = o_valid ? fmaf(__uint_as_float(r[j + 1]), s1.x, s1.y) + a1 : 0.f;
+          }
+          if (p.out16 && o_in) {
+            uint32_t h2_[8], l2_[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const float y0 = v[j] < 0.f ? v[j] * p.slope : v[j], y1 = v[j + 1] < 0.f ? v[j + 1] * p.slope : v[j + 1];
+              split16x2(y0, y1, h2_[j >> 1], l2_[j >> 1]);
+            }
+#pragma unroll
+            for (int q4 = 0; q4 < 2; ++q4) {
+              reinterpret_cast<uint4*>(p.out16 + rowoff + c0)[q4] = make_uint4(h2_[4 * q4], h2_[4 * q4 + 1], h2_[4 * q4 + 2], h2_[4 * q4 + 3]);
+              reinterpret_cast<uint4*>(p.out16 + plane + rowoff + c0)[q4] = make_uint4(l2_[4 * q4], l2_[4 * q4 + 1], l2_[4 * q4 + 2], l2_[4 * q4 + 3]);
+            }
+          }
+          if (p.acc32 && o_in) {
+            if (p.acc_mode == TC_ACC_ADD_DIV) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = o_valid ? (old[j] + v[j]) / p.acc_div : 0.f;
+              if (p.acc_store) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) __stcs(p.acc32 + ((size_t)b * C + cc * 32 + c0 + j) * p.L + t, v[j]);
+              }
+              if (p.out16b) {
+                uint32_t h2_[8], l2_[8];
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  const float y0 = v[j] < 0.f ? v[j] * p.slope : v[j], y1 = v[j + 1] < 0.f ? v[j + 1] * p.slope : v[j + 1];
+                  split16x2(y0, y1, h2_[j >> 1], l2_[j >> 1]);
+                }
+#pragma unroll
+                for (int q4 = 0; q4 < 2; ++q4) {
+                  reinterpret_cast<uint4*>(p.out16b + rowoff + c0)[q4] = make_uint4(h2_[4 * q4], h2_[4 * q4 + 1], h2_[4 * q4 + 2], h2_[4 * q4 + 3]);
+                  reinterpret_cast<uint4*>(p.out16b + plane + rowoff + c0)[q4] = make_uint4(l2_[4 * q4], l2_[4 * q4 + 1], l2_[4 * q4 + 2], l2_[4 * q4 + 3]);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) __stcs(p.acc32 + ((size_t)b * C + cc * 32 + c0 + j) * p.L + t, old[j] + v[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace tc
+}  // namespace cube

@@ -85,7 +85,9 @@ def _categorical(y: torch.Tensor, u: torch.Tensor = None) -> torch.Tensor:
     y = y.to(torch.float32).contiguous()
     Cn = y.shape[-1]
     if u is None:
-        u = torch.empty_like(y).uniform_(1e-5, 1.0 - 1e-5)
+        # full-range uniforms: truncating them to (1e-5, 1 - 1e-5) caps the Gumbel noise at 11.5 and measurably starves the
+        # rare classes (chi-square test in tests/test_gpu_parity.py); u = 0 maps to -inf (never picked), as it should
+        u = torch.rand_like(y)
     u = u.to(y.device, torch.float32).contiguous()
     idx = torch.empty(y.shape[:-1], dtype=torch.int64, device=y.device)
     with torch.cuda.device(y.device):
