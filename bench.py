@@ -36,6 +36,8 @@ WORKLOADS = {
     "hifigan": ("hifigan", 64, 919, "BASELINE configs[2]: batch=64 x 10 s (F=919), HiFi-GAN generator (neb-noft rates [3,5,4,4])"),
     # configs[3]: 256 utterances of 2-15 s on rank 0, LPT-sharded over the ranks, NCCL scatter/gather (strong scaling)
     "ragged": ("hifigan", 256, 0, "BASELINE configs[3]: batch=256 variable-length (2-15 s) utterances, HiFi-GAN generator, sharded across the ranks via NCCL p2p scatter/gather"),
+    # the reference API's call shape: ONE utterance per call (cube/api.py:45-66)
+    "api1": ("hifigan", 1, 0, "batch-1 latency (TTSCube.__call__ shape): one utterance of 2 s / 10 s, HiFi-GAN and ParallelWaveNet student, host in -> host out"),
     # configs[0]: CPU only (the autoregressive ClariNet teacher), timed on a few steady-state samples and extrapolated
     "teacher_cpu": ("teacher", 1, 173, "BASELINE configs[0]: single 2 s utterance (F=173, T=44288), 80-bin mel, ClariNet teacher (autoregressive) on CPU PyTorch"),
 }
@@ -374,6 +376,71 @@ def run_teacher_cpu(args, desc, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_api1(args, desc, rank, local):
+    """Batch-1 latency - the reference API's only call shape (`TTSCube.__call__` synthesises ONE utterance per call,
+    cube/api.py:45-66; the frontend is batch-1 by construction, cube/networks/modules.py:945-953): one utterance of 2 s and
+    of 10 s through each vocoder, host mel in -> host int16/float audio out (`forward_host`) and device-resident.
+    Reports the median latency, the real-time factor and how many tiles each HiFi-GAN stage offers the 148 SMs."""
+    if rank != 0:
+        return
+    import tts_cube_b200 as cube
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    out = {}
+    iters = max(5, args.steps)
+    for arch in ("hifigan", "student"):
+        weights, wdesc = load_weights(arch)
+        if arch == "student":
+            voc = cube.ParallelWaveNetVocoder(weights[0], weights[1]).to(dev)
+            hop = 256
+        else:
+            voc = cube.CubeGenerator(weights[1]).to(dev)
+            voc.load_state_dict(weights[0])
+            hop = 240
+        for secs in (2.0, 10.0):
+            F = int(round(secs * SR / hop))
+            T = voc.out_len(F)
+            mel, z = synth_inputs(arch, 1, F, seed=4321)
+            mel_d, z_d = mel.to(dev), (z.to(dev) if z is not None else None)
+            mel_h, z_h = mel.pin_memory(), (z.pin_memory() if z is not None else None)
+            out_h = torch.empty(1, T, dtype=torch.float32).pin_memory()
+            call_d = (lambda: voc(mel_d, z_d)) if arch == "student" else (lambda: voc(mel_d))
+            call_h = (lambda: voc.forward_host(mel_h, z_h, out=out_h)) if arch == "student" else (lambda: voc.forward_host(mel_h, out=out_h))
+            with torch.no_grad():
+                for _ in range(max(3, args.warmup)):
+                    call_d(); call_h()
+                torch.cuda.synchronize()
+                dts, hts = [], []
+                for _ in range(iters):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); call_d(); e1.record(); torch.cuda.synchronize()
+                    dts.append(e0.elapsed_time(e1))
+                    t0 = time.perf_counter(); call_h(); hts.append(1e3 * (time.perf_counter() - t0))
+            d_ms, h_ms = statistics.median(dts), statistics.median(hts)
+            out[f"{arch}_{int(secs)}s"] = {"frames": F, "samples": T, "device_ms": d_ms, "host_e2e_ms": h_ms,
+                                           "rtf_device": (T / SR) / (d_ms / 1e3), "rtf_host_e2e": (T / SR) / (h_ms / 1e3),
+                                           "launches": voc._ensure().launches()}
+        del voc
+        torch.cuda.empty_cache()
+    # HiFi-GAN stage occupancy at B=1, 10 s: scheduled tiles per launch vs 148 SMs (neb-noft rates [3,5,4,4])
+    L, occ = int(round(10.0 * SR / 240)), {}
+    for i, (u, k) in enumerate(zip(HIFIGAN_NEB_CONFIG["upsample_rates"], HIFIGAN_NEB_CONFIG["upsample_kernel_sizes"])):
+        L = (L - 1) * u - 2 * ((k - u) // 2) + k
+        ch = 512 >> (i + 1)
+        rows = {256: 128, 128: 128, 64: 256, 32: 512}[ch]
+        occ[f"stage{i}_{ch}ch"] = {"rows": L, "tiles_unfused": (L + rows - 1) // rows,
+                                   "tiles_fused_step_k11": (L + rows - 11) // (rows - 10) if ch <= 64 else None}
+    ref = out["hifigan_10s"]
+    print(json.dumps({
+        "metric": "audio samples/sec", "value": ref["samples"] / (ref["device_ms"] / 1e3), "unit": "samples/s", "n_gpus": 1, "steps": iters,
+        "warmup": max(3, args.warmup), "ms_per_step": ref["device_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 in/out; tcgen05 split-fp16", "data": "synthetic; shipped checkpoints when staged", "rtf": ref["rtf_device"],
+        "config": {"workload": desc, "headline": "hifigan_10s (value / ms_per_step); every case under `cases`"},
+        "e2e": {"value": ref["samples"] / (ref["host_e2e_ms"] / 1e3), "unit": "samples/s", "h2d_bytes_per_step": 80 * ref["frames"] * 4,
+                "d2h_bytes_per_step": ref["samples"] * 4, "copies_declared": True},
+        "cases": out, "sm_tiles_at_batch1_10s": occ, "gpu_launches": ref["launches"] * iters, "lib": cube.build_info()}), flush=True)
+
+
 def run_ragged(args, desc, rank, world, local):
     """configs[3]: rank 0 owns 256 variable-length mels; tts_cube_b200.synthesize shards them (LPT), scatters the
     padded mel blocks, every rank vocodes its shard, rank 0 gathers the audio.  Strong scaling: the work is fixed."""
@@ -478,6 +545,9 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.workload == "ragged":
         run_ragged(args, desc, rank, world, local)
+        return
+    if args.workload == "api1":
+        run_api1(args, desc, rank, local)
         return
 
     import torch.distributed as dist

@@ -171,6 +171,33 @@ def test_hifigan_host_call_matches_device_call(dev):
     assert torch.equal(c, H.wav_to_int16(a))
 
 
+def test_forward_host_graph_replay(dev):
+    """cube_voc_forward_host replays a CUDA graph from the second call with a geometry on: results must stay identical to
+    the stream-launched device call for changing inputs and changing n_frames masks (the graph bakes in neither), after
+    a geometry change (workspace growth invalidates older graphs) and when coming back to the first geometry."""
+    cfg = dict(H.CONFIG_V1)
+    sd = H.random_state_dict(cfg, seed=21, std=0.3, g_scale=0.125)
+    g = _gen(cfg, sd, dev, 1)
+    ssd, tsd = C.random_state_dict("student", 3, blocks=[6, 1, 1, 2]), C.random_state_dict("teacher", 4, blocks=[1])
+    v = _student(ssd, tsd, dev, 1)
+    for rnd, (B, F_) in enumerate([(2, 9), (2, 9), (2, 9), (3, 14), (2, 9), (2, 9)]):
+        mel = H.synthetic_mel(B, F_, seed=300 + rnd)
+        frames = [F_] + [max(1, F_ - 2 - rnd - b) for b in range(1, B)]
+        with torch.no_grad():
+            a = g(mel.to(dev), n_frames=frames).cpu().squeeze(1)
+        assert torch.equal(g.forward_host(mel.pin_memory(), n_frames=frames), a), (rnd, "hifigan")
+        i16 = g.forward_host(mel, n_frames=frames, int16=True)
+        assert torch.equal(i16, H.wav_to_int16(a)), (rnd, "hifigan int16")
+        melc = C.synthetic_mel01(B, F_, seed=400 + rnd)
+        z = torch.randn(B, 1, F_ * 256, generator=torch.Generator().manual_seed(500 + rnd))
+        with torch.no_grad():
+            d_ = v(melc.to(dev), z.to(dev), n_frames=frames).cpu().squeeze(1)
+        assert torch.equal(v.forward_host(melc.pin_memory(), z.pin_memory(), n_frames=frames), d_), (rnd, "student")
+    import tts_cube_b200 as cube
+    with pytest.raises(cube.CubeVocError):
+        g.forward_host(H.synthetic_mel(2, 9, seed=1), n_frames=[9, 10])        # n_frames > Fmax is still rejected on the replay path
+
+
 @pytest.mark.parametrize("math", MATHS)
 def test_hifigan_full_size_properties(dev, neb, math):
     """BASELINE config 3 shape (10 s utterances) through size-independent properties: batch items are

@@ -18,7 +18,6 @@
 #include "heads.cuh"
 #include "tc_conv.cuh"
 #include "tc_block.cuh"
-#include "tc_block_pair.cuh"
 #include "tc_rbstep.cuh"
 #include "wavernn.cuh"
 #include "melspec.cuh"
@@ -103,6 +102,15 @@ struct cube_voc {
   int16_t* d_wav16 = nullptr; size_t d_wav16_cap = 0;
   cudaStream_t own_stream = nullptr;
   int64_t launches = 0;
+  // CUDA graphs of the host-buffer call (cube_voc_forward_host): one per (B, Fmax, noise?, int16?).  The launch plan
+  // depends only on that key (n_frames only changes the masks, uploaded from a pinned buffer the graph's memcpy node
+  // reads at replay time); every device buffer the plan touches is owned by the handle, and `alloc_gen` counts their
+  // (re)allocations - a graph captured under an older generation is discarded.
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t gen = 0; int64_t launches = 0; int seen = 0; };
+  std::map<std::vector<int64_t>, GraphEntry> graphs;
+  uint64_t alloc_gen = 0;
+  int* h_lens_pin = nullptr; size_t h_lens_pin_cap = 0;
+  bool lens_from_pinned = false;            // set while capturing / replaying a graph
   int sm_count = 148;
   // profiling
   bool profile = false;
@@ -158,6 +166,7 @@ static int ws_get(cube_voc* h, const char* name, size_t n_floats, float** out) {
   if (b.bytes < need) {
     if (b.p) CU_TRY(cudaFree(b.p));
     b.p = nullptr; b.bytes = 0;
+    ++h->alloc_gen;
     CU_TRY(cudaMalloc(&b.p, need));
     b.bytes = need;
   }
@@ -774,13 +783,9 @@ static int64_t hifigan_len(const cube_voc_config& c, int64_t L, int upto) {
   return L;
 }
 
-static int upload_lens(cube_voc* h, const int32_t* n_frames, int B, int64_t Fmax, int nlevels, cudaStream_t st) {
+// valid length of every utterance at every level of the network -> h->h_lens [nlevels][B] (host only)
+static int fill_lens(cube_voc* h, const int32_t* n_frames, int B, int64_t Fmax, int nlevels) {
   const size_t need = (size_t)nlevels * B;
-  if (h->lens_cap < need) {
-    if (h->d_lens) CU_TRY(cudaFree(h->d_lens));
-    CU_TRY(cudaMalloc(&h->d_lens, need * sizeof(int)));
-    h->lens_cap = need;
-  }
   h->h_lens.resize(need);
   for (int b = 0; b < B; ++b) {
     int64_t f = n_frames ? n_frames[b] : Fmax;
@@ -792,6 +797,42 @@ static int upload_lens(cube_voc* h, const int32_t* n_frames, int B, int64_t Fmax
       h->h_lens[(size_t)l * B + b] = (int)L;
     }
   }
+  return 0;
+}
+
+static int lens_levels(const cube_voc* h) {
+  return h->cfg.arch == CUBE_VOC_HIFIGAN ? h->cfg.n_ups + 1 : h->cfg.n_upsample + 1;
+}
+
+// graph path: the masks travel through a pinned host buffer whose address is baked into the graph's memcpy node
+static int stage_lens_pinned(cube_voc* h, const int32_t* n_frames, int B, int64_t Fmax) {
+  const int nlevels = lens_levels(h);
+  if (fill_lens(h, n_frames, B, Fmax, nlevels)) return 1;
+  const size_t need = (size_t)nlevels * B;
+  if (h->h_lens_pin_cap < need) {
+    if (h->h_lens_pin) CU_TRY(cudaFreeHost(h->h_lens_pin));
+    h->h_lens_pin = nullptr; h->h_lens_pin_cap = 0;
+    ++h->alloc_gen;
+    CU_TRY(cudaMallocHost((void**)&h->h_lens_pin, std::max<size_t>(need, 256) * sizeof(int)));
+    h->h_lens_pin_cap = std::max<size_t>(need, 256);
+  }
+  memcpy(h->h_lens_pin, h->h_lens.data(), need * sizeof(int));
+  return 0;
+}
+
+static int upload_lens(cube_voc* h, const int32_t* n_frames, int B, int64_t Fmax, int nlevels, cudaStream_t st) {
+  const size_t need = (size_t)nlevels * B;
+  if (h->lens_cap < need) {
+    if (h->d_lens) CU_TRY(cudaFree(h->d_lens));
+    ++h->alloc_gen;
+    CU_TRY(cudaMalloc(&h->d_lens, need * sizeof(int)));
+    h->lens_cap = need;
+  }
+  if (h->lens_from_pinned) {     // graph capture / replay: stage_lens_pinned() has filled the pinned buffer
+    CU_TRY(cudaMemcpyAsync(h->d_lens, h->h_lens_pin, need * sizeof(int), cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+  if (fill_lens(h, n_frames, B, Fmax, nlevels)) return 1;
   CU_TRY(cudaMemcpyAsync(h->d_lens, h->h_lens.data(), need * sizeof(int), cudaMemcpyHostToDevice, st));
   return 0;
 }
@@ -1414,61 +1455,53 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
         bp.B = B; bp.T = T; bp.t_tiles = (T + tc::BM - 1) / tc::BM;
         bp.lens = lens_T; bp.skip = sk; bp.skip_set = (i == 0); bp.scale = rs;
         bp.skip16 = (i == nb - 1) ? s16 : nullptr;
-        static bool attrb[64] = {false};
-        if (!attrb[h->device & 63]) {
-          CU_TRY(cudaFuncSetAttribute(tc::tc_block_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::BLK_SMEM));
-          CU_TRY(cudaFuncSetAttribute(tc::tc_block_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::BLK_SMEM));
-          CU_TRY(cudaFuncSetAttribute(tc::tc_block_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::BLK_SMEM));
-          CU_TRY(cudaFuncSetAttribute(tc::tc_block_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::BLK_SMEM));
-          attrb[h->device & 63] = true;
-        }
-        const long long tiles = (long long)bp.t_tiles * B;
-        const int grid = (int)std::min<long long>(tiles, h->sm_count);
         const bool q8 = fp8 && fl.has_tc_front && fl.tc_gate[i].Wimg8;
         if (q8) { bp.tmH8 = tm_h8; bp.tmC8 = tm_c8; bp.W1q = fl.tc_gate[i].Wimg8; bp.h8_out = h8b; }
-        static int pairv = -1;      // CTA-pair (cta_group::2) version of the block kernel; CUBE_TC_PAIR=0: one CTA per tile
+        static int pairv = -1;      // CTA-pair (cta_group::2) tiling of the block kernel; CUBE_TC_PAIR=0: one CTA per tile
         if (pairv < 0) { const char* e = getenv("CUBE_TC_PAIR"); pairv = (e && e[0] == '0') ? 0 : 1; }
-        if (block_stats_on()) pairv = 0;                                  // the instrumented build is single-CTA
-        if (pairv == 1) {
-          static bool attrp[64] = {false};
-          if (!attrp[h->device & 63]) {
-            CU_TRY(cudaFuncSetAttribute(tc::tc_block_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PAIR_SMEM));
-            CU_TRY(cudaFuncSetAttribute(tc::tc_block_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PAIR_SMEM));
-            CU_TRY(cudaFuncSetAttribute(tc::tc_block_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PAIR_SMEM));
-            CU_TRY(cudaFuncSetAttribute(tc::tc_block_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PAIR_SMEM));
-            attrp[h->device & 63] = true;
+        static int direct = -1;     // pair only: both CTAs' loads complete on the leader's barrier (no relay thread)
+        if (direct < 0) { const char* e = getenv("CUBE_PAIR_DIRECT"); direct = (e && e[0] == '1') ? 1 : 0; }
+        const bool stats = block_stats_on();                             // instrumented build: wait cycles of CTA 0
+        if (stats) bp.stats = block_stats_buf();
+        // the 2 x 2 x 2 (+ direct) instantiations of the one kernel template
+        auto launch = [&](auto kernel, bool pair) -> int {
+          const size_t smem = pair ? tc::PAIR_SMEM : tc::BLK_SMEM;
+          static std::map<std::pair<const void*, int>, bool> attr_done;
+          const auto key = std::make_pair((const void*)kernel, h->device);
+          if (!attr_done[key]) {
+            CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done[key] = true;
           }
-          bp.t_tiles = (T + 2 * tc::BM - 1) / (2 * tc::BM);               // a pair's tile is 256 rows
-          const long long ptiles = (long long)bp.t_tiles * B;
           cudaLaunchConfig_t cfg;
           memset(&cfg, 0, sizeof(cfg));
-          cfg.gridDim = dim3(2 * (unsigned)std::min<long long>(ptiles, h->sm_count / 2));
-          cfg.blockDim = dim3(tc::NUM_THREADS);
-          cfg.dynamicSmemBytes = tc::PAIR_SMEM;
-          cfg.stream = st;
           cudaLaunchAttribute at[1];
-          at[0].id = cudaLaunchAttributeClusterDimension;
-          at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-          cfg.attrs = at; cfg.numAttrs = 1;
-          static int direct = -1;     // both CTAs' loads complete on the leader's barrier (no relay thread); CUBE_PAIR_DIRECT=0: relay
-          if (direct < 0) { const char* e = getenv("CUBE_PAIR_DIRECT"); direct = (e && e[0] == '1') ? 1 : 0; }
-          if (direct) {
-            if (q8) CU_TRY(cudaLaunchKernelEx(&cfg, tc::tc_block_pair_kernel<true, true>, bp));
-            else CU_TRY(cudaLaunchKernelEx(&cfg, tc::tc_block_pair_kernel<false, true>, bp));
+          if (pair) {
+            bp.t_tiles = (T + 2 * tc::BM - 1) / (2 * tc::BM);           // a pair's tile is 256 rows
+            const long long ptiles = (long long)bp.t_tiles * B;
+            cfg.gridDim = dim3(2 * (unsigned)std::min<long long>(ptiles, h->sm_count / 2));
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
           } else {
-            if (q8) CU_TRY(cudaLaunchKernelEx(&cfg, tc::tc_block_pair_kernel<true, false>, bp));
-            else CU_TRY(cudaLaunchKernelEx(&cfg, tc::tc_block_pair_kernel<false, false>, bp));
+            const long long tiles = (long long)bp.t_tiles * B;
+            cfg.gridDim = dim3((unsigned)std::min<long long>(tiles, h->sm_count));
           }
-        } else
-        if (block_stats_on()) {   // instrumented build: wait cycles of CTA 0 per barrier, printed by block_stats_dump()
-          bp.stats = block_stats_buf();
-          if (q8) tc::tc_block_kernel<true, true><<<grid, tc::NUM_THREADS, tc::BLK_SMEM, st>>>(bp);
-          else tc::tc_block_kernel<true, false><<<grid, tc::NUM_THREADS, tc::BLK_SMEM, st>>>(bp);
-        } else if (q8) {
-          tc::tc_block_kernel<false, true><<<grid, tc::NUM_THREADS, tc::BLK_SMEM, st>>>(bp);
+          cfg.blockDim = dim3(tc::NUM_THREADS);
+          cfg.dynamicSmemBytes = smem;
+          cfg.stream = st;
+          CU_TRY(cudaLaunchKernelEx(&cfg, kernel, bp));
+          return 0;
+        };
+        int lrc;
+        if (pairv == 1) {
+          if (stats) lrc = q8 ? launch(tc::tc_block_kernel<true, true, false, true>, true) : launch(tc::tc_block_kernel<true, false, false, true>, true);
+          else if (direct) lrc = q8 ? launch(tc::tc_block_kernel<true, true, true, false>, true) : launch(tc::tc_block_kernel<true, false, true, false>, true);
+          else lrc = q8 ? launch(tc::tc_block_kernel<true, true, false, false>, true) : launch(tc::tc_block_kernel<true, false, false, false>, true);
         } else {
-          tc::tc_block_kernel<false, false><<<grid, tc::NUM_THREADS, tc::BLK_SMEM, st>>>(bp);
+          if (stats) lrc = q8 ? launch(tc::tc_block_kernel<false, true, false, true>, false) : launch(tc::tc_block_kernel<false, false, false, true>, false);
+          else lrc = q8 ? launch(tc::tc_block_kernel<false, true, false, false>, false) : launch(tc::tc_block_kernel<false, false, false, false>, false);
         }
+        if (lrc) return 1;
         lx.check();
         lx.end();
         std::swap(h16, h16b);          // the block's output is the next block's input
@@ -1728,10 +1761,11 @@ static int ensure_device(cube_voc* h) {
 }
 
 template <typename T>
-static int grow(T** p, size_t* cap, size_t need_bytes) {
+static int grow(T** p, size_t* cap, size_t need_bytes, uint64_t* gen = nullptr) {
   if (*cap >= need_bytes) return 0;
   if (*p) CU_TRY(cudaFree(*p));
   *p = nullptr; *cap = 0;
+  if (gen) ++*gen;
   CU_TRY(cudaMalloc((void**)p, need_bytes));
   *cap = need_bytes;
   return 0;
@@ -1869,25 +1903,72 @@ int cube_voc_forward(cube_voc_t* h, const float* mel, const int32_t* n_frames, c
   return forward_student(h, mel, n_frames, noise, wav, wav_i16, B, Fmax, st);
 }
 
+// CUBE_GRAPH=0 disables the CUDA-graph replay of the host-buffer call
+static bool graphs_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CUBE_GRAPH"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 int cube_voc_forward_host(cube_voc_t* h, const float* mel, const int32_t* n_frames, const float* noise, float* wav,
                           int16_t* wav_i16, int B, int64_t Fmax) {
   if (!h) return fail("null handle");
   if (!h->finalized) return fail("forward before finalize");
   if (!mel || (!wav && !wav_i16)) return fail("null mel / no output buffer");
   if (B < 1 || Fmax < 1) return fail("empty batch");
+  if (h->cfg.arch == CUBE_VOC_WAVERNN) return fail("use cube_wavernn_forward for a WaveRNN handle");
+  if (h->cfg.arch == CUBE_VOC_PWN_STUDENT && !noise) return fail("the IAF student needs `noise` (z ~ N(0,1), [B,1,T])");
   if (ensure_device(h)) return 1;
   const int64_t T = cube_voc_out_len(h, Fmax);
   const size_t mel_b = (size_t)B * h->cfg.num_mels * Fmax * sizeof(float);
   const size_t wav_n = (size_t)B * T;
-  if (grow(&h->d_mel, &h->d_mel_cap, mel_b) || grow(&h->d_wav, &h->d_wav_cap, wav_n * sizeof(float))) return 1;
-  if (wav_i16 && grow(&h->d_wav16, &h->d_wav16_cap, wav_n * sizeof(int16_t))) return 1;
+  if (grow(&h->d_mel, &h->d_mel_cap, mel_b, &h->alloc_gen) || grow(&h->d_wav, &h->d_wav_cap, wav_n * sizeof(float), &h->alloc_gen)) return 1;
+  if (wav_i16 && grow(&h->d_wav16, &h->d_wav16_cap, wav_n * sizeof(int16_t), &h->alloc_gen)) return 1;
+  if (noise && grow(&h->d_noise, &h->d_noise_cap, wav_n * sizeof(float), &h->alloc_gen)) return 1;
   cudaStream_t st = h->own_stream;
   CU_TRY(cudaMemcpyAsync(h->d_mel, mel, mel_b, cudaMemcpyHostToDevice, st));
-  if (noise) {
-    if (grow(&h->d_noise, &h->d_noise_cap, wav_n * sizeof(float))) return 1;
-    CU_TRY(cudaMemcpyAsync(h->d_noise, noise, wav_n * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (noise) CU_TRY(cudaMemcpyAsync(h->d_noise, noise, wav_n * sizeof(float), cudaMemcpyHostToDevice, st));
+
+  // ---- the forward itself: replay a captured graph when one exists for this geometry, capture one on the second call
+  // with a geometry (the first call runs eagerly and sizes the workspace), else launch kernel by kernel ----
+  bool done = false;
+  if (graphs_enabled() && !h->profile && !block_stats_on()) {
+    const std::vector<int64_t> key = {B, Fmax, noise ? 1 : 0, wav_i16 ? 1 : 0};
+    cube_voc::GraphEntry& ge = h->graphs[key];
+    if (ge.exec && ge.gen != h->alloc_gen) { cudaGraphExecDestroy(ge.exec); ge.exec = nullptr; }
+    if (ge.exec || ge.seen >= 1) {
+      if (stage_lens_pinned(h, n_frames, B, Fmax)) return 1;        // validates n_frames, fills the pinned mask buffer
+      if (ge.exec && ge.gen != h->alloc_gen) { cudaGraphExecDestroy(ge.exec); ge.exec = nullptr; }   // the pinned buffer moved
+    }
+    if (!ge.exec && ge.seen >= 1) {
+      const uint64_t gen0 = h->alloc_gen;
+      cudaGraph_t graph = nullptr;
+      h->lens_from_pinned = true;
+      cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+      int rc = 1;
+      if (e == cudaSuccess) {
+        rc = cube_voc_forward(h, h->d_mel, n_frames, noise ? h->d_noise : nullptr, h->d_wav, wav_i16 ? h->d_wav16 : nullptr, B, Fmax, st);
+        e = cudaStreamEndCapture(st, &graph);
+      }
+      h->lens_from_pinned = false;
+      if (e == cudaSuccess && rc == 0 && graph && gen0 == h->alloc_gen) {
+        cudaGraphExec_t ex = nullptr;
+        if (cudaGraphInstantiate(&ex, graph, 0) == cudaSuccess) { ge.exec = ex; ge.gen = h->alloc_gen; ge.launches = h->launches; }
+      }
+      if (graph) cudaGraphDestroy(graph);
+      if (!ge.exec) {
+        cudaGetLastError();                                         // a failed capture must not poison the eager path
+        if (rc) return rc;
+      }
+    }
+    if (ge.exec) {
+      CU_TRY(cudaGraphLaunch(ge.exec, st));
+      h->launches = ge.launches;
+      done = true;
+    }
+    ++ge.seen;
   }
-  if (cube_voc_forward(h, h->d_mel, n_frames, noise ? h->d_noise : nullptr, h->d_wav, wav_i16 ? h->d_wav16 : nullptr, B, Fmax, st)) return 1;
+  if (!done && cube_voc_forward(h, h->d_mel, n_frames, noise ? h->d_noise : nullptr, h->d_wav, wav_i16 ? h->d_wav16 : nullptr, B, Fmax, st)) return 1;
   if (wav) CU_TRY(cudaMemcpyAsync(wav, h->d_wav, wav_n * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (wav_i16) CU_TRY(cudaMemcpyAsync(wav_i16, h->d_wav16, wav_n * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
@@ -1979,6 +2060,8 @@ void cube_voc_destroy(cube_voc_t* h) {
   if (h->d_wav) cudaFree(h->d_wav);
   if (h->d_wav16) cudaFree(h->d_wav16);
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (h->h_lens_pin) cudaFreeHost(h->h_lens_pin);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }

@@ -11,19 +11,35 @@
 // TMEM: two 256-column regions X, Y.  Per tile (parity p swaps the roles): GEMM1 n-tile 0 -> R0, GEMM1 n-tile 1 ->
 // R1, GEMM2 (both K halves) -> R0 again once its gate epilogue has drained it.  The next tile starts in this tile's
 // R1, which is free long before this tile's res/skip epilogue runs.
-// smem: 3-stage ring of 48 KB (A hi/lo 8 KB each by TMA + one 256-row weight chunk hi/lo 16 KB each by bulk copy;
-// GEMM2 stages carry weights only), a 64 KB buffer for one K-half of o as four K-major SWIZZLE_64B A tiles per plane,
-// 6 KB of folded (de-scale, bias) pairs.  Roles as in tc_conv_kernel: warp 0 TMA, warp 1 MMA, warps 2-17 epilogue.
+// smem: a ring of stages (A hi/lo 8 KB each by TMA + this CTA's weight rows hi/lo by bulk copy; GEMM2 stages carry weights
+// only), a 64 KB buffer for one K-half of o as four K-major SWIZZLE_64B A tiles per plane, 6 KB of folded (de-scale, bias)
+// pairs.  Roles as in tc_conv_kernel: warp 0 TMA, warp 1 MMA, warps 2-17 epilogue.
 #pragma once
 #include "tc_conv.cuh"
 
 namespace cube {
 namespace tc {
 
-constexpr int BLK_STAGES = 3;
-constexpr int BLK_STAGE_BYTES = 2 * A_TILE_BYTES + 2 * (256 * BK * 2);    // 48 KB
-constexpr int BLK_O_BYTES = 2 * 4 * A_TILE_BYTES;                         // 4 chunks x (hi, lo) = 64 KB
-constexpr int BLK_SMEM = BLK_STAGES * BLK_STAGE_BYTES + BLK_O_BYTES + 1024 + 256 + 768 * 8;
+// One kernel text, two tilings (template parameter PAIR):
+//   PAIR = false: one CTA per 128-row tile, tcgen05 cta_group::1 (M = 128); 3 ring stages of 48 KB (A 16 KB + weights 32 KB).
+//   PAIR = true : a 2-CTA cluster per 256-row tile, cta_group::2 (M = 256).  Each CTA stages its own 128 rows of A (and
+//                 keeps its own rows of o, h, skip: the epilogues are the same code) but only HALF of every weight tile -
+//                 the pair's tensor cores exchange the halves - so a stage is 32 KB (4 stages) and the L2 -> shared-memory
+//                 bytes per output row drop by a third.  The leader's (rank 0) MMA thread issues every MMA and owns the
+//                 accumulator / o-buffer hand-shakes: the peer's epilogue warps arrive remotely (relaxed, cluster scope -
+//                 the release form compiles to MEMBAR.ALL.GPU) on the leader's barriers, tcgen05.commit multicasts
+//                 completions to both CTAs.
+template <bool PAIR> struct BlkCfg {
+  static constexpr int NST = PAIR ? 4 : 3;                                            // ring stages
+  static constexpr int B_BYTES = (PAIR ? 128 : 256) * BK * 2;                         // this CTA's weight rows, one fp16 plane
+  static constexpr int STG = 2 * A_TILE_BYTES + 2 * B_BYTES;                          // 32 / 48 KB
+  static constexpr int O_BYTES = 2 * 4 * A_TILE_BYTES;                                // 4 chunks x (hi, lo) = 64 KB
+  static constexpr int SMEM = NST * STG + O_BYTES + 1024 + 512 + 768 * 8;
+  static constexpr int TILE_ROWS = PAIR ? 2 * BM : BM;
+};
+constexpr int BLK_O_BYTES = BlkCfg<false>::O_BYTES;
+constexpr int BLK_SMEM = BlkCfg<false>::SMEM;
+constexpr int PAIR_SMEM = BlkCfg<true>::SMEM;
 static_assert(BK == 32, "tc_block_kernel is written for 32-channel K chunks (SWIZZLE_64B)");
 
 struct BlockParams {
@@ -60,26 +76,69 @@ struct BlockParams {
     }                                                              \
   } while (0)
 
+__device__ __forceinline__ void umma_f8_2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// epilogue -> leader's MMA thread: local arrive on the leader, remote (relaxed, cluster scope) from the peer
+__device__ __forceinline__ void pair_arrive(uint64_t* bar, uint32_t crank) {
+  if (crank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0);
+}
+
+// the MMA / commit of the tiling
+template <bool PAIR>
+__device__ __forceinline__ void blk_mma_f16(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  if constexpr (PAIR) umma_f16_2(d, da, db, idesc, acc); else umma_f16(d, da, db, idesc, acc);
+}
+template <bool PAIR>
+__device__ __forceinline__ void blk_mma_f8(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  if constexpr (PAIR) umma_f8_2(d, da, db, idesc, acc); else umma_f8(d, da, db, idesc, acc);
+}
+template <bool PAIR>
+__device__ __forceinline__ void blk_commit(uint64_t* bar) {
+  if constexpr (PAIR) umma_commit_2(bar); else umma_commit(bar);
+}
+
+// DIRECT (PAIR only): the TMA / bulk loads of BOTH CTAs complete on the LEADER's stage barrier (a shared::cluster address),
+// which the leader arms with the bytes of both stages; without it the peer's MMA warp relays "my stage has landed" (wait own
+// barrier -> remote arrive on the leader's `pfull`), a polling loop + DSMEM hop per stage.
+// STATS: instrumented build (CUBE_BLOCK_STATS=1): CTA 0's cycles per barrier wait.
 // 18 warps: the SM sub-partitions hold 5,5,4,4 of them, so 16384/5 -> 96 registers per thread is the hardware cap
-template <bool STATS, bool Q8>
+template <bool PAIR, bool Q8, bool DIRECT = false, bool STATS = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_constant__ BlockParams p) {
+  static_assert(PAIR || !DIRECT, "DIRECT is a protocol of the CTA pair");
   long long st_acc[STATS ? 8 : 1] = {0};
   const long long st_begin = STATS ? clock64() : 0;
+  (void)st_acc; (void)st_begin;
   constexpr int BN = 256;
-  constexpr int B_BYTES = BN * BK * 2;             // 16 KB per plane
+  constexpr int B_BYTES = BlkCfg<PAIR>::B_BYTES;   // this CTA's weight rows (all 256, or its HALF of the pair's tile), one fp16 plane
+  constexpr int NST = BlkCfg<PAIR>::NST;
+  constexpr int STG = BlkCfg<PAIR>::STG;
+  constexpr int TILE_ROWS = BlkCfg<PAIR>::TILE_ROWS;
+  constexpr int NARR = PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS;      // epilogue warps that arrive on the leader's hand-shake barriers
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;               // 0 = leader: issues the MMAs
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* o_smem = smem + BLK_STAGES * BLK_STAGE_BYTES;      // [4 chunks][hi 8 KB | lo 8 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(o_smem + BLK_O_BYTES);
-  uint64_t* full = bars;                       // [3]
-  uint64_t* empty = bars + BLK_STAGES;         // [3]
-  uint64_t* acc_full = bars + 2 * BLK_STAGES;  // [2] region holds a finished accumulator        (MMA -> epilogue)
-  uint64_t* acc_free = acc_full + 2;           // [2] region drained                             (epilogue -> MMA, 16 warps)
-  uint64_t* o_full = acc_free + 2;             // [1] o half is in smem                          (epilogue -> MMA, 16 warps)
+  uint8_t* o_smem = smem + NST * STG;      // [4 chunks][hi 8 KB | lo 8 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(o_smem + BlkCfg<PAIR>::O_BYTES);
+  uint64_t* full = bars;                       // [4] this CTA's stage has landed
+  uint64_t* empty = bars + NST;                // [4] (commit multicast: both CTAs)
+  uint64_t* pfull = bars + 2 * NST;            // [4] leader only: the PEER's stage has landed (relayed by its MMA warp)
+  uint64_t* acc_full = bars + 3 * NST;         // [2] region holds a finished accumulator        (commit multicast -> both epilogues)
+  uint64_t* acc_free = acc_full + 2;           // [2] leader only: region drained by BOTH CTAs   (2 x 16 warps)
+  uint64_t* o_full = acc_free + 2;             // [1] leader only: o half staged in BOTH CTAs    (2 x 16 warps)
   uint64_t* o_free = o_full + 1;               // [1] GEMM2 has read the o half                  (MMA -> epilogue)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
   uint64_t* hbar = o_free + 2;                 // [16] per epilogue warp: its residual rows have landed in shared memory
-  float2* sb1 = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [512] gate: folded exp2 factors
+  float2* sb1 = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [512] gate: folded exp2 factors
   float2* sb2 = sb1 + 512;                                                           // [256] res/skip
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,9 +148,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmH);
     prefetch_tmap(&p.tmC);
-    for (int s = 0; s < BLK_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int r = 0; r < 2; ++r) { mbar_init(&acc_full[r], 1); mbar_init(&acc_free[r], NUM_EPI_WARPS); }
-    mbar_init(o_full, NUM_EPI_WARPS);
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&pfull[s], 1); }
+    for (int r = 0; r < 2; ++r) { mbar_init(&acc_full[r], 1); mbar_init(&acc_free[r], NARR); }
+    mbar_init(o_full, NARR);
     mbar_init(o_free, 1);
     for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(&hbar[w], 1);
     prefetch_tmap(&p.tmHin32);
@@ -99,7 +158,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
     if (Q8) { prefetch_tmap(&p.tmH8); prefetch_tmap(&p.tmC8); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) { if constexpr (PAIR) tmem_alloc2(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
   {  // folded per-column constants, once per CTA (this CTA owns all 512 + 256 columns)
     constexpr float LOG2E = 1.4426950408889634f;
     for (int i = threadIdx.x; i < 512; i += NUM_THREADS) {
@@ -110,6 +169,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();    // both CTAs' barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -117,9 +177,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
     // =========================== TMA producer ===========================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int tt = tile % p.t_tiles, b = tile / p.t_tiles;
-        const int t0 = tt * BM;
+        const int t0 = tt * TILE_ROWS + (int)crank * BM;       // this CTA's 128 rows of the tile
         for (int nt = 0; nt < 2; ++nt) {                       // GEMM1, one 256-column n-tile at a time
           const __half* wt = p.W1 + (size_t)nt * nch1 * 2 * (BN * BK);
           int chunk = 0;
@@ -128,35 +188,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
             const int row = cond ? t0 : t0 + p.off0 + tap * p.dil;
             const int ncc = cond ? p.c_chunks : p.h_chunks;
             for (int cc = 0; cc < ncc; ++cc, ++chunk, ++it) {
-              const int st = it % BLK_STAGES;
-              BLK_WAIT(&empty[st], ((it / BLK_STAGES) & 1) ^ 1, 0);
-              uint8_t* sb = smem + st * BLK_STAGE_BYTES;
-              mbar_expect_tx(&full[st], BLK_STAGE_BYTES);
+              const int st = it % NST;
+              BLK_WAIT(&empty[st], ((it / NST) & 1) ^ 1, 0);
+              uint8_t* sb = smem + st * STG;
+              const uint32_t fbar = DIRECT ? mapa_u32(smem_u32(&full[st]), 0) : smem_u32(&full[st]);
+              if (!DIRECT) mbar_expect_tx(&full[st], STG);
+              else if (crank == 0) mbar_expect_tx(&full[st], 2 * STG);
               const CUtensorMap* tm = cond ? &p.tmC : &p.tmH;
-              tma_load_3d(sb, tm, &full[st], cc * BK, row, b);
+              tma_load_3d_bar(sb, tm, fbar, cc * BK, row, b);
               if constexpr (Q8) {
                 // a_hi fp16 (8 KB) | e4m3(a_hi) (4 KB) | e5m2(16 a_lo) (4 KB); one 32 KB weight image
                 const CUtensorMap* tm8 = cond ? &p.tmC8 : &p.tmH8;
-                tma_load_3d(sb + A_TILE_BYTES, tm8, &full[st], cc * BK, row, b);
-                tma_load_3d(sb + A_TILE_BYTES + A_TILE_BYTES / 2, tm8, &full[st], cc * BK, row, p.B + b);
-                bulk_load(sb + 2 * A_TILE_BYTES, p.W1q + ((size_t)nt * nch1 + chunk) * (2 * B_BYTES), 2 * B_BYTES, &full[st]);
+                tma_load_3d_bar(sb + A_TILE_BYTES, tm8, fbar, cc * BK, row, b);
+                tma_load_3d_bar(sb + A_TILE_BYTES + A_TILE_BYTES / 2, tm8, fbar, cc * BK, row, p.B + b);
+                // rows [128 crank, +128) of each of the three sub-images of the 32 KB chunk image
+                const uint8_t* wq = p.W1q + ((size_t)nt * nch1 + chunk) * 32768;
+                bulk_load_bar(sb + 2 * A_TILE_BYTES, wq + crank * B_BYTES, B_BYTES, fbar);
+                bulk_load_bar(sb + 2 * A_TILE_BYTES + B_BYTES, wq + 16384 + crank * (B_BYTES / 2), B_BYTES / 2, fbar);
+                bulk_load_bar(sb + 2 * A_TILE_BYTES + B_BYTES + B_BYTES / 2, wq + 24576 + crank * (B_BYTES / 2), B_BYTES / 2, fbar);
               } else {
-                tma_load_3d(sb + A_TILE_BYTES, tm, &full[st], cc * BK, row, p.B + b);
-                const __half* wc = wt + (size_t)chunk * 2 * (BN * BK);
-                bulk_load(sb + 2 * A_TILE_BYTES, wc, B_BYTES, &full[st]);
-                bulk_load(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, &full[st]);
+                tma_load_3d_bar(sb + A_TILE_BYTES, tm, fbar, cc * BK, row, p.B + b);
+                const __half* wc = wt + (size_t)chunk * 2 * (BN * BK) + (size_t)crank * (BN / 2) * BK /* crank = 0 without PAIR */;   // this CTA's 128 weight rows
+                bulk_load_bar(sb + 2 * A_TILE_BYTES, wc, B_BYTES, fbar);
+                bulk_load_bar(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, fbar);
               }
             }
           }
         }
         for (int ch = 0; ch < 8; ++ch, ++it) {                 // GEMM2: weights only (its A operand is o, on chip)
-          const int st = it % BLK_STAGES;
-          BLK_WAIT(&empty[st], ((it / BLK_STAGES) & 1) ^ 1, 1);
-          uint8_t* sb = smem + st * BLK_STAGE_BYTES;
-          mbar_expect_tx(&full[st], 2 * B_BYTES);
-          const __half* wc = p.W2 + (size_t)ch * 2 * (BN * BK);
-          bulk_load(sb + 2 * A_TILE_BYTES, wc, B_BYTES, &full[st]);
-          bulk_load(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, &full[st]);
+          const int st = it % NST;
+          BLK_WAIT(&empty[st], ((it / NST) & 1) ^ 1, 1);
+          uint8_t* sb = smem + st * STG;
+          const uint32_t fbar = DIRECT ? mapa_u32(smem_u32(&full[st]), 0) : smem_u32(&full[st]);
+          if (!DIRECT) mbar_expect_tx(&full[st], 2 * B_BYTES);
+          else if (crank == 0) mbar_expect_tx(&full[st], 4 * B_BYTES);
+          const __half* wc = p.W2 + (size_t)ch * 2 * (BN * BK) + (size_t)crank * (BN / 2) * BK /* crank = 0 without PAIR */;
+          bulk_load_bar(sb + 2 * A_TILE_BYTES, wc, B_BYTES, fbar);
+          bulk_load_bar(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, fbar);
         }
       }
       if (STATS && p.stats && blockIdx.x == 0) {
@@ -167,12 +235,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN, BM);
+    if (lane == 0 && crank != 0 && DIRECT) {
+      // peer CTA, direct protocol: its loads complete on the leader's barriers; nothing to do here
+    } else if (lane == 0 && crank != 0) {      // (crank != 0 only exists with PAIR)
+      // peer CTA: it issues no MMA; this thread relays "my stage has landed" to the leader
+      uint32_t it = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step)
+        for (int n = 2 * nch1 + 8; n > 0; --n, ++it) {
+          const int st = it % NST;
+          mbar_wait(&full[st], (it / NST) & 1);
+          mbar_arrive_remote(&pfull[st], 0);
+        }
+    } else if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, TILE_ROWS);    // M = 128, or 256 across the pair
       uint32_t it = 0, titer = 0;
       uint32_t free_ph[2] = {0, 0};        // completed-phase counters of acc_free[r] this thread has consumed
       uint32_t ofull_ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++titer) {
         const int r0 = titer & 1, r1 = r0 ^ 1;      // region roles of this tile
         for (int nt = 0; nt < 2; ++nt) {
           const int rg = nt == 0 ? r0 : r1;
@@ -186,36 +265,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
             const bool cond = tap == p.taps;
             const int ncc = cond ? p.c_chunks : p.h_chunks;
             for (int cc = 0; cc < ncc; ++cc, ++it) {
-              const int st = it % BLK_STAGES;
-              BLK_WAIT(&full[st], (it / BLK_STAGES) & 1, 2);
+              const int st = it % NST;
+              BLK_WAIT(&full[st], (it / NST) & 1, 2);
+              if constexpr (PAIR && !DIRECT) mbar_wait(&pfull[st], (it / NST) & 1);
               tc_fence_after();
-              const uint32_t a_hi = smem_u32(smem + st * BLK_STAGE_BYTES), a_lo = a_hi + A_TILE_BYTES;
+              const uint32_t a_hi = smem_u32(smem + st * STG), a_lo = a_hi + A_TILE_BYTES;
               const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + B_BYTES;
               const int ksteps = (cond && cc == ncc - 1) ? p.c_last_ksteps : (BK / 16);
               if constexpr (Q8) {
                 // hi*hi in fp16 (K = 16 per MMA), then the two 2^-11-weight corrections as ONE 8-bit MMA each (K = 32):
                 // e4m3(a_hi) x e4m3(w_lo)  and  e5m2(16 a_lo) x e4m3(w_hi / 16)  -> 4 MMAs per chunk instead of 6
                 for (int ks = 0; ks < ksteps; ++ks) {
-                  umma_f16(d_tmem, make_desc(a_hi + ks * 32), make_desc(b_hi + ks * 32), idesc, accumulate);
+                  blk_mma_f16<PAIR>(d_tmem, make_desc(a_hi + ks * 32), make_desc(b_hi + ks * 32), idesc, accumulate);
                   accumulate = 1;
                 }
                 const uint32_t a8_hi = a_hi + A_TILE_BYTES, a8_lo = a8_hi + A_TILE_BYTES / 2;
                 const uint32_t b8_lo = b_hi + B_BYTES, b8_hi = b8_lo + B_BYTES / 2;
-                umma_f8(d_tmem, make_desc32(a8_hi), make_desc32(b8_lo), make_idesc_f8(BN, BM, 0), 1);
-                umma_f8(d_tmem, make_desc32(a8_lo), make_desc32(b8_hi), make_idesc_f8(BN, BM, 1), 1);
+                blk_mma_f8<PAIR>(d_tmem, make_desc32(a8_hi), make_desc32(b8_lo), make_idesc_f8(BN, TILE_ROWS, 0), 1);
+                blk_mma_f8<PAIR>(d_tmem, make_desc32(a8_lo), make_desc32(b8_hi), make_idesc_f8(BN, TILE_ROWS, 1), 1);
               } else {
                 for (int ks = 0; ks < ksteps; ++ks) {
                   const uint32_t ko = ks * 32;
-                  umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
-                  umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
-                  umma_f16(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                  blk_mma_f16<PAIR>(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
+                  blk_mma_f16<PAIR>(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+                  blk_mma_f16<PAIR>(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
                   accumulate = 1;
                 }
               }
-              umma_commit(&empty[st]);
+              blk_commit<PAIR>(&empty[st]);
             }
           }
-          umma_commit(&acc_full[rg]);
+          blk_commit<PAIR>(&acc_full[rg]);
         }
         // GEMM2 into r0 (drained by the gate epilogue of n-tile 0): K half kh uses the o half the epilogue staged
         {
@@ -228,23 +308,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
             ++ofull_ph;
             tc_fence_after();
             for (int c4 = 0; c4 < 4; ++c4, ++it) {
-              const int st = it % BLK_STAGES;
-              BLK_WAIT(&full[st], (it / BLK_STAGES) & 1, 6);
+              const int st = it % NST;
+              BLK_WAIT(&full[st], (it / NST) & 1, 6);
+              if constexpr (PAIR && !DIRECT) mbar_wait(&pfull[st], (it / NST) & 1);
               tc_fence_after();
               const uint32_t a_hi = smem_u32(o_smem + c4 * 2 * A_TILE_BYTES), a_lo = a_hi + A_TILE_BYTES;
-              const uint32_t b_hi = smem_u32(smem + st * BLK_STAGE_BYTES) + 2 * A_TILE_BYTES, b_lo = b_hi + B_BYTES;
+              const uint32_t b_hi = smem_u32(smem + st * STG) + 2 * A_TILE_BYTES, b_lo = b_hi + B_BYTES;
               for (int ks = 0; ks < BK / 16; ++ks) {
                 const uint32_t ko = ks * 32;
-                umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
-                umma_f16(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
-                umma_f16(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                blk_mma_f16<PAIR>(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
+                blk_mma_f16<PAIR>(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+                blk_mma_f16<PAIR>(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
                 accumulate = 1;
               }
-              umma_commit(&empty[st]);
+              blk_commit<PAIR>(&empty[st]);
             }
-            umma_commit(o_free);          // the o half may be overwritten
+            blk_commit<PAIR>(o_free);          // the o half may be overwritten
           }
-          umma_commit(&acc_full[r0]);     // r|s accumulator complete
+          blk_commit<PAIR>(&acc_full[r0]);     // r|s accumulator complete
         }
       }
       if (STATS && p.stats && blockIdx.x == 0) {
@@ -260,9 +341,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
     uint32_t titer = 0;
     uint32_t full_ph[2] = {0, 0};           // uses of acc_full[r] consumed so far
     uint32_t ofree_ph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++titer) {
       const int tt = tile % p.t_tiles, b = tile / p.t_tiles;
-      const int t = tt * BM + row;
+      const int t = tt * TILE_ROWS + (int)crank * BM + row;
       const int r0 = titer & 1, r1 = r0 ^ 1;
       const int len = p.lens ? min(p.lens[b], p.T) : p.T;
       const bool in_range = t < p.T, valid = t < len;
@@ -308,7 +389,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
         // the accumulator region is drained: hand it back before waiting for the o buffer
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_free[rg]);
+        if (lane == 0) pair_arrive(&acc_free[rg], crank);
         // the o buffer is free once GEMM2 has consumed the previous half (first half ever: passes at once)
         if (STATS) st_acc[5] += clock64() - g_t0;       // gate math (TMEM load .. region handed back)
         BLK_WAIT(o_free, (ofree_ph & 1) ^ 1, 2 + nt);
@@ -330,7 +411,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
         }
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(o_full);
+        if (lane == 0) pair_arrive(o_full, crank);
       }
       // ---------------- res/skip epilogue (GEMM2 result in region r0) ----------------
       // Every warp owns 32 residual channels [32 grp, +32) and the 32 skip channels of the same index, for its 32 rows.
@@ -350,7 +431,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
         const int ew = warp - 2;
         uint8_t* piece_hi = o_smem + grp * 2 * A_TILE_BYTES + q * 2048;      // rows [32 q, +32) of K chunk grp
         uint8_t* piece_lo = piece_hi + A_TILE_BYTES;
-        const int tw = tt * BM + q * 32;                                     // first time step of this warp's rows
+        const int tw = tt * TILE_ROWS + (int)crank * BM + q * 32;            // first time step of this warp's rows
         float old[32];             // only a flow's last block needs the running skip total (relu -> fp16 planes)
         if (last_block) {
 #pragma unroll
@@ -419,7 +500,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
           if (ci == 1) {           // last TMEM read of this warp: hand the region back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_free[r0]);
+            if (lane == 0) pair_arrive(&acc_free[r0], crank);
           }
           const uint32_t* hp = reinterpret_cast<const uint32_t*>(hv);
           const uint32_t* lp = reinterpret_cast<const uint32_t*>(lv);
@@ -466,9 +547,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();    // no CTA of the pair exits while the other may still signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
