@@ -1459,11 +1459,9 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
         if (q8) { bp.tmH8 = tm_h8; bp.tmC8 = tm_c8; bp.W1q = fl.tc_gate[i].Wimg8; bp.h8_out = h8b; }
         static int pairv = -1;      // CTA-pair (cta_group::2) tiling of the block kernel; CUBE_TC_PAIR=0: one CTA per tile
         if (pairv < 0) { const char* e = getenv("CUBE_TC_PAIR"); pairv = (e && e[0] == '0') ? 0 : 1; }
-        static int direct = -1;     // pair only: both CTAs' loads complete on the leader's barrier (no relay thread)
-        if (direct < 0) { const char* e = getenv("CUBE_PAIR_DIRECT"); direct = (e && e[0] == '1') ? 1 : 0; }
         const bool stats = block_stats_on();                             // instrumented build: wait cycles of CTA 0
         if (stats) bp.stats = block_stats_buf();
-        // the 2 x 2 x 2 (+ direct) instantiations of the one kernel template
+        // the PAIR x Q8 x STATS instantiations of the one kernel template
         auto launch = [&](auto kernel, bool pair) -> int {
           const size_t smem = pair ? tc::PAIR_SMEM : tc::BLK_SMEM;
           static std::map<std::pair<const void*, int>, bool> attr_done;
@@ -1494,12 +1492,11 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
         };
         int lrc;
         if (pairv == 1) {
-          if (stats) lrc = q8 ? launch(tc::tc_block_kernel<true, true, false, true>, true) : launch(tc::tc_block_kernel<true, false, false, true>, true);
-          else if (direct) lrc = q8 ? launch(tc::tc_block_kernel<true, true, true, false>, true) : launch(tc::tc_block_kernel<true, false, true, false>, true);
-          else lrc = q8 ? launch(tc::tc_block_kernel<true, true, false, false>, true) : launch(tc::tc_block_kernel<true, false, false, false>, true);
+          if (stats) lrc = q8 ? launch(tc::tc_block_kernel<true, true, true>, true) : launch(tc::tc_block_kernel<true, false, true>, true);
+          else lrc = q8 ? launch(tc::tc_block_kernel<true, true, false>, true) : launch(tc::tc_block_kernel<true, false, false>, true);
         } else {
-          if (stats) lrc = q8 ? launch(tc::tc_block_kernel<false, true, false, true>, false) : launch(tc::tc_block_kernel<false, false, false, true>, false);
-          else lrc = q8 ? launch(tc::tc_block_kernel<false, true, false, false>, false) : launch(tc::tc_block_kernel<false, false, false, false>, false);
+          if (stats) lrc = q8 ? launch(tc::tc_block_kernel<false, true, true>, false) : launch(tc::tc_block_kernel<false, false, true>, false);
+          else lrc = q8 ? launch(tc::tc_block_kernel<false, true, false>, false) : launch(tc::tc_block_kernel<false, false, false>, false);
         }
         if (lrc) return 1;
         lx.check();

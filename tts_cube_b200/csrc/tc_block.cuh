@@ -105,14 +105,14 @@ __device__ __forceinline__ void blk_commit(uint64_t* bar) {
   if constexpr (PAIR) umma_commit_2(bar); else umma_commit(bar);
 }
 
-// DIRECT (PAIR only): the TMA / bulk loads of BOTH CTAs complete on the LEADER's stage barrier (a shared::cluster address),
-// which the leader arms with the bytes of both stages; without it the peer's MMA warp relays "my stage has landed" (wait own
-// barrier -> remote arrive on the leader's `pfull`), a polling loop + DSMEM hop per stage.
+// PAIR: the peer's MMA warp relays "my stage has landed" (wait own barrier -> remote arrive on the leader's `pfull`).  Letting the
+// peer's loads complete on the LEADER's barrier directly was tried in round 2 and hangs: a 1-D cp.async.bulk (the weight
+// images) may only signal an mbarrier of the CTA whose shared memory it fills (only the .cta_group::2 TENSOR form may
+// signal the peer CTA's barrier).
 // STATS: instrumented build (CUBE_BLOCK_STATS=1): CTA 0's cycles per barrier wait.
 // 18 warps: the SM sub-partitions hold 5,5,4,4 of them, so 16384/5 -> 96 registers per thread is the hardware cap
-template <bool PAIR, bool Q8, bool DIRECT = false, bool STATS = false>
+template <bool PAIR, bool Q8, bool STATS = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_constant__ BlockParams p) {
-  static_assert(PAIR || !DIRECT, "DIRECT is a protocol of the CTA pair");
   long long st_acc[STATS ? 8 : 1] = {0};
   const long long st_begin = STATS ? clock64() : 0;
   (void)st_acc; (void)st_begin;
@@ -191,9 +191,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
               const int st = it % NST;
               BLK_WAIT(&empty[st], ((it / NST) & 1) ^ 1, 0);
               uint8_t* sb = smem + st * STG;
-              const uint32_t fbar = DIRECT ? mapa_u32(smem_u32(&full[st]), 0) : smem_u32(&full[st]);
-              if (!DIRECT) mbar_expect_tx(&full[st], STG);
-              else if (crank == 0) mbar_expect_tx(&full[st], 2 * STG);
+              const uint32_t fbar = smem_u32(&full[st]);
+              mbar_expect_tx(&full[st], STG);
               const CUtensorMap* tm = cond ? &p.tmC : &p.tmH;
               tma_load_3d_bar(sb, tm, fbar, cc * BK, row, b);
               if constexpr (Q8) {
@@ -219,9 +218,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
           const int st = it % NST;
           BLK_WAIT(&empty[st], ((it / NST) & 1) ^ 1, 1);
           uint8_t* sb = smem + st * STG;
-          const uint32_t fbar = DIRECT ? mapa_u32(smem_u32(&full[st]), 0) : smem_u32(&full[st]);
-          if (!DIRECT) mbar_expect_tx(&full[st], 2 * B_BYTES);
-          else if (crank == 0) mbar_expect_tx(&full[st], 4 * B_BYTES);
+          const uint32_t fbar = smem_u32(&full[st]);
+          mbar_expect_tx(&full[st], 2 * B_BYTES);
           const __half* wc = p.W2 + (size_t)ch * 2 * (BN * BK) + (size_t)crank * (BN / 2) * BK /* crank = 0 without PAIR */;
           bulk_load_bar(sb + 2 * A_TILE_BYTES, wc, B_BYTES, fbar);
           bulk_load_bar(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, fbar);
@@ -235,9 +233,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0 && crank != 0 && DIRECT) {
-      // peer CTA, direct protocol: its loads complete on the leader's barriers; nothing to do here
-    } else if (lane == 0 && crank != 0) {      // (crank != 0 only exists with PAIR)
+    if (lane == 0 && crank != 0) {             // (crank != 0 only exists with PAIR)
       // peer CTA: it issues no MMA; this thread relays "my stage has landed" to the leader
       uint32_t it = 0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step)
@@ -267,7 +263,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
             for (int cc = 0; cc < ncc; ++cc, ++it) {
               const int st = it % NST;
               BLK_WAIT(&full[st], (it / NST) & 1, 2);
-              if constexpr (PAIR && !DIRECT) mbar_wait(&pfull[st], (it / NST) & 1);
+              if constexpr (PAIR) BLK_WAIT(&pfull[st], (it / NST) & 1, 2);
               tc_fence_after();
               const uint32_t a_hi = smem_u32(smem + st * STG), a_lo = a_hi + A_TILE_BYTES;
               const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + B_BYTES;
@@ -310,7 +306,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
             for (int c4 = 0; c4 < 4; ++c4, ++it) {
               const int st = it % NST;
               BLK_WAIT(&full[st], (it / NST) & 1, 6);
-              if constexpr (PAIR && !DIRECT) mbar_wait(&pfull[st], (it / NST) & 1);
+              if constexpr (PAIR) BLK_WAIT(&pfull[st], (it / NST) & 1, 6);
               tc_fence_after();
               const uint32_t a_hi = smem_u32(o_smem + c4 * 2 * A_TILE_BYTES), a_lo = a_hi + A_TILE_BYTES;
               const uint32_t b_hi = smem_u32(smem + st * STG) + 2 * A_TILE_BYTES, b_lo = b_hi + B_BYTES;
