@@ -2,7 +2,11 @@
 """Top stall-sample instructions of each kernel in an .ncu-rep (source page, SASS view)."""
 import csv, io, subprocess, sys
 src, topn = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 25
-out = subprocess.run(["ncu", "-i", src, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+if src.endswith(".gz"):      # `ncu -i <rep> --page source --csv | gzip` exported on the GPU box
+    import gzip
+    out = gzip.open(src, "rt").read()
+else:
+    out = subprocess.run(["ncu", "-i", src, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 blocks, cur = [], None
 for row in csv.reader(io.StringIO(out)):
     if row and row[0] == "Kernel Name":

@@ -17,7 +17,9 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
         "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_bytes.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_fmaheavy.sum", "smsp__inst_executed.sum"]
+        "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_fmaheavy.sum", "smsp__inst_executed.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum"]
 
 
 def launches(src, dst):
@@ -46,7 +48,11 @@ def launches(src, dst):
 
 
 def full(src, dst):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """src: an .ncu-rep, or the `ncu -i <rep> --page raw --csv` text exported on the GPU box (*.csv)"""
+    if src.endswith(".csv"):
+        out = open(src).read()
+    else:
+        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rd = list(csv.reader(io.StringIO(out)))
     hdr, units, data = rd[0], rd[1], rd[2:]
     with open(dst, "w") as f:
@@ -55,8 +61,11 @@ def full(src, dst):
             d = dict(zip(hdr, row))
             f.write(f"## {d.get('Kernel Name', '?')[:100]}  (id {d.get('ID')})\n\n| metric | value | unit |\n|---|---|---|\n")
             for k in KEYS:
-                if k in d:
-                    f.write(f"| {k} | {d[k]} | {units[hdr.index(k)]} |\n")
+                for hname in hdr:                       # newer ncu prefixes some columns with a section name
+                    if hname == k or hname.endswith("." + k):
+                        if d[hname] != "":
+                            f.write(f"| {k} | {d[hname]} | {units[hdr.index(hname)]} |\n")
+                        break
             f.write("\n")
     print(open(dst).read())
 

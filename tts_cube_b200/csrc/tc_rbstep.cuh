@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
         if (x_next >= my_tiles) return;
         const uint32_t par = (x_next & 1) ^ 1;
         if (block) mbar_wait(xempty, par);
-        else if (!mbar_try_wait(xempty, par)) return;
+        else if (!mbar_test_wait(xempty, par)) return;      // a probe, never a sleep: this thread is also feeding the weight ring
         const int tile = (int)blockIdx.x + x_next * (int)gridDim.x;
         const int tt = tile % p.t_tiles, b = tile / p.t_tiles;
         const int r0 = tt * R_OUT - h2 - h1;                 // first row of the x window
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
       auto weights = [&](const __half* W) {                 // the k * NCH images of one conv, in the MMA thread's order
         for (int img = 0; img < p.k * NCH; ++img, ++iw) {
           const int s = iw % WS;
-          while (!mbar_try_wait(&wempty[s], ((iw / WS) & 1) ^ 1)) try_x(false);
+          while (!mbar_test_wait(&wempty[s], ((iw / WS) & 1) ^ 1)) try_x(false);
           mbar_expect_tx(&wfull[s], Cfg::WIMG);
           bulk_load(wring + s * Cfg::WIMG, W + (size_t)img * (Cfg::WIMG / 2), Cfg::WIMG, &wfull[s]);
         }
