@@ -59,7 +59,12 @@ template <int TN, bool CG2 = false> struct Cfg {
   static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int NSTAGE = (190 * 1024 / STAGE) > 8 ? 8 : (190 * 1024 / STAGE);
   static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256 + TN * 8;
-  static constexpr int TMEM_COLS = 2 * MSUB * TN;              // 256 or 512: double-buffered accumulators
+  // CAT (tiles narrower than 256 columns, single CTA): the hi*hi and hi*lo passes are ONE MMA of N = 2 TN on the weight
+  // image [w_hi rows | w_lo rows] - one fetch of a_hi for two products (shared memory feeds the tensor core at ~64 B/clk,
+  // which is what bounds these MMAs) - into separate column halves that the epilogue adds; lo*hi follows with N = TN
+  static constexpr bool CAT = TN < 256 && !CG2;
+  static constexpr int ACC_COLS = CAT ? 2 * TN : TN;           // accumulator columns per 128-row sub-tile
+  static constexpr int TMEM_COLS = 2 * MSUB * ACC_COLS;        // 256 or 512: double-buffered accumulators
 };
 // Window mode: the taps of a dilated conv are overlapping row windows of the SAME tensor, so the A operand of a
 // channel chunk is staged ONCE as a window of CTA_ROWS + (taps-1)*dil rows and every tap's MMA reads it through a
@@ -421,6 +426,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
   constexpr int STAGE_BYTES = WIN ? (SA * A_SLOT + SB * B_SLOT + STAGES - 1) / STAGES : Cfg<TN, CG2>::STAGE;
   constexpr int B_TILE_BYTES = Cfg<TN, CG2>::B_BYTES;
   constexpr int BN = TN;
+  constexpr bool CAT = Cfg<TN, CG2>::CAT;
+  constexpr int ACCW = Cfg<TN, CG2>::ACC_COLS;
   constexpr int MSUB = Cfg<TN, CG2>::MSUB;
   constexpr int A_BYTES = Cfg<TN, CG2>::A_BYTES;
   constexpr int CTA_ROWS = MSUB * BM;               // rows this CTA owns in a scheduled tile
@@ -558,12 +565,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
         }
       } else if (WIN) {
         constexpr uint32_t idesc = make_idesc(TN, BM);
+        constexpr uint32_t idesc_cat = make_idesc(CAT ? 2 * TN : TN, BM);
         uint32_t ia = 0, ib = 0, titer = 0;
         for (int tile = tile0; tile < total_tiles; tile += tile_step, ++titer) {
           const uint32_t acc = titer & 1, aph = (titer >> 1) & 1;
           mbar_wait(&tempty[acc], aph ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * (MSUB * BN);
+          const uint32_t d_tmem = tmem_base + acc * (MSUB * ACCW);
           uint32_t accumulate = 0;
           for (int s = 0; s < p.nseg; ++s) {
             const TcSeg sg = p.seg[s];
@@ -583,10 +591,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
 #pragma unroll
                   for (int ms = 0; ms < MSUB; ++ms) {
                     const uint32_t a_hi = a_tap + ms * A_TILE_BYTES, a_lo = a_hi + A_LO_OFF;
-                    const uint32_t d = d_tmem + ms * BN;
-                    umma_f16(d, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
-                    umma_f16(d, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
-                    umma_f16(d, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                    const uint32_t d = d_tmem + ms * ACCW;
+                    if constexpr (CAT) {     // [w_hi | w_lo] is one K-major tile of 2 TN rows (the lo image follows the hi image)
+                      umma_f16(d, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc_cat, accumulate);
+                      umma_f16(d, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                    } else {
+                      umma_f16(d, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
+                      umma_f16(d, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+                      umma_f16(d, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                    }
                   }
                   accumulate = 1;
                 }
@@ -599,12 +612,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
         }
       } else {
         constexpr uint32_t idesc = make_idesc(TN, CG2 ? 2 * BM : BM);
+        constexpr uint32_t idesc_cat = make_idesc(CAT ? 2 * TN : TN, BM);
         uint32_t it = 0, titer = 0;
         for (int tile = tile0; tile < total_tiles; tile += tile_step, ++titer) {
           const uint32_t acc = titer & 1, aph = (titer >> 1) & 1;
           mbar_wait(&tempty[acc], aph ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * (MSUB * BN);
+          const uint32_t d_tmem = tmem_base + acc * (MSUB * ACCW);
           uint32_t accumulate = 0;
           for (int s = 0; s < p.nseg; ++s) {
             const TcSeg sg = p.seg[s];
@@ -624,8 +638,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
 #pragma unroll
                   for (int ms = 0; ms < MSUB; ++ms) {
                     const uint32_t a_hi = a_hi0 + ms * A_TILE_BYTES, a_lo = a_hi + A_BYTES;
-                    const uint32_t d = d_tmem + ms * BN;
-                    if constexpr (CG2) {
+                    const uint32_t d = d_tmem + ms * ACCW;
+                    if constexpr (CAT) {
+                      umma_f16(d, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc_cat, accumulate);
+                      umma_f16(d, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                    } else if constexpr (CG2) {
                       umma_f16_2(d, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
                       umma_f16_2(d, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
                       umma_f16_2(d, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
@@ -680,7 +697,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
         asm volatile("bar.sync 1, 512;" ::: "memory");
         sb_nt = nt;
       }
-      const uint32_t taddr = tmem_base + (acc * MSUB + msub) * BN + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + (acc * MSUB + msub) * ACCW + ((uint32_t)(q * 32) << 16);
       const int len = p.lens ? min(p.lens[b], p.T) : p.T;
       const bool in_range = t < p.T;
       const bool valid = t < len;
@@ -725,6 +742,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
         for (int cc = sub * CPS; cc < sub * CPS + CPS; cc += CW) {
           uint32_t r[CW];
           if constexpr (CW == 16) tmem_ld16(taddr + cc, r); else tmem_ld8(taddr + cc, r);
+          uint32_t r2[CAT ? CW : 1];                       // CAT: the a_hi*w_lo products, TN columns further on
+          if constexpr (CAT) { if constexpr (CW == 16) tmem_ld16(taddr + BN + cc, r2); else tmem_ld8(taddr + BN + cc, r2); }
           uint32_t rh[CW / 2], rl[CW / 2];
           float old[CW];
           if (p.res16 && o_in) {
@@ -747,6 +766,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
             for (int j = 0; j < CW; ++j) old[j] = 0.f;
           }
           tmem_ld_wait();
+          if constexpr (CAT) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          }
           float v[CW];
 #pragma unroll
           for (int j = 0; j < CW; j += 2) {

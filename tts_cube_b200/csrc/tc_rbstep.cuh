@@ -19,7 +19,13 @@
 //     producer :  X(it)  W1(it)  W2(it-1)
 //     MMA      :  M1(it)         M2(it-1)          (conv1 of the next tile is issued BEFORE conv2 of this one, so the
 //     epilogue :  E1(it)         E2(it-1)           tensor pipe runs M1(it) while E1(it-1)'s a1 tiles are being written)
-// TMEM: two buffers of [acc1: NSUB*C | acc2: NSUB*C] columns = 512.
+// Operand fetch is the limit of these narrow MMAs: shared memory feeds the tensor core at ~64 B/clk (ncu: a 128x32x16 MMA
+// costs ~80 cycles = 4 KB of A + 1 KB of B, for 16 cycles of math), so the hi*hi and hi*lo passes share ONE fetch of a_hi:
+// the weight image [w_hi rows | w_lo rows] is a single B tile of N = 2C, its two products land in separate column halves
+// of the accumulator (the epilogue adds them), and lo*hi follows with N = C into the first half - 2 MMAs and 2 A fetches
+// per K step instead of 3.
+// TMEM: [acc1: NSUB*2C | acc2: NSUB*2C] columns = 512, single-buffered: the interleaved schedule leaves E1(it) a whole
+// M2(it-1) to drain acc1 before M1(it+1) needs it, and E2(it-1) a whole M1(it+1) to drain acc2 before M2(it).
 #pragma once
 #include "tc_conv.cuh"
 
@@ -40,8 +46,8 @@ template <int C, int NSUB> struct RbCfg {
   static constexpr int WS = WS_ > 12 ? 12 : WS_;                   // weight ring depth
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM = 1024 + XWIN + MID + WS * WIMG + BAR_BYTES + 2 * C * 8;
-  static constexpr int ACC = NSUB * C;                             // columns of one accumulator
-  static_assert(4 * ACC == 512, "TMEM budget");
+  static constexpr int ACC = NSUB * 2 * C;                         // columns of one accumulator: per sub-tile [hi*hi + lo*hi | hi*lo]
+  static_assert(2 * ACC == 512, "TMEM budget");
   static_assert(WS >= 4, "weight ring too shallow");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -77,14 +83,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
   uint64_t* xempty = bars + 1;           // [1]
   uint64_t* wfull = bars + 2;            // [WS]
   uint64_t* wempty = wfull + WS;         // [WS]
-  uint64_t* a1full = wempty + WS;        // [2]  MMA -> epilogue
-  uint64_t* a1free = a1full + 2;         // [2]  epilogue (16 warps) -> MMA
-  uint64_t* a2full = a1free + 2;         // [2]
-  uint64_t* a2free = a2full + 2;         // [2]
-  uint64_t* midfull = a2free + 2;        // [1]  epilogue (16 warps) -> MMA
+  uint64_t* a1full = wempty + WS;        // [1]  MMA -> epilogue
+  uint64_t* a1free = a1full + 1;         // [1]  epilogue (16 warps) -> MMA
+  uint64_t* a2full = a1free + 1;         // [1]
+  uint64_t* a2free = a2full + 1;         // [1]
+  uint64_t* midfull = a2free + 1;        // [1]  epilogue (16 warps) -> MMA
   uint64_t* midfree = midfull + 1;       // [1]  MMA -> epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(midfree + 1);
-  static_assert((2 + 2 * WS + 10) * 8 + 8 <= Cfg::BAR_BYTES, "barrier block");
+  static_assert((2 + 2 * WS + 6) * 8 + 8 <= Cfg::BAR_BYTES, "barrier block");
   float2* sb1 = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);   // [C] (de-scale, bias) of conv1
   float2* sb2 = sb1 + C;
 
@@ -99,10 +105,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
     prefetch_tmap(&p.tmX);
     mbar_init(xfull, 1); mbar_init(xempty, 1);
     for (int s = 0; s < WS; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&a1full[a], 1); mbar_init(&a1free[a], NUM_EPI_WARPS);
-      mbar_init(&a2full[a], 1); mbar_init(&a2free[a], NUM_EPI_WARPS);
-    }
+    mbar_init(a1full, 1); mbar_init(a1free, NUM_EPI_WARPS);
+    mbar_init(a2full, 1); mbar_init(a2free, NUM_EPI_WARPS);
     mbar_init(midfull, NUM_EPI_WARPS); mbar_init(midfree, 1);
     fence_barrier_init();
   }
@@ -158,7 +162,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(C, BM);
+      constexpr uint32_t idesc_cat = make_idesc(2 * C, BM);     // a_hi x [w_hi | w_lo]
+      constexpr uint32_t idesc_one = make_idesc(C, BM);         // a_lo x w_hi
       uint32_t iw = 0;
       // one conv over the NSUB sub-tiles: A planes at a_base (+ cc*2*plane_bytes), tap j starts `tap_rows * j` rows in
       auto conv = [&](uint32_t d_tmem, uint32_t a_base, uint32_t plane_bytes, int tap_rows) {
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
             const int s = iw % WS;
             mbar_wait(&wfull[s], (iw / WS) & 1);
             tc_fence_after();
-            const uint32_t b_hi = smem_u32(wring + s * Cfg::WIMG), b_lo = b_hi + Cfg::WIMG / 2;
+            const uint32_t b_hi = smem_u32(wring + s * Cfg::WIMG);      // [w_hi: C rows][w_lo: C rows], one K-major tile of 2C rows
             const uint32_t a_hi0 = a_base + (uint32_t)(cc * 2) * plane_bytes + (uint32_t)(tap * tap_rows) * ROW_BYTES;
             const uint32_t a_lo0 = a_hi0 + plane_bytes;
 #pragma unroll
@@ -177,10 +182,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
 #pragma unroll
               for (int ms = 0; ms < NSUB; ++ms) {
                 const uint32_t a_hi = a_hi0 + ms * A_TILE_BYTES + ko, a_lo = a_lo0 + ms * A_TILE_BYTES + ko;
-                const uint32_t d = d_tmem + ms * C;
-                umma_f16(d, make_desc(a_hi), make_desc(b_hi + ko), idesc, accumulate);
-                umma_f16(d, make_desc(a_hi), make_desc(b_lo + ko), idesc, 1);
-                umma_f16(d, make_desc(a_lo), make_desc(b_hi + ko), idesc, 1);
+                const uint32_t d = d_tmem + ms * 2 * C;
+                umma_f16(d, make_desc(a_hi), make_desc(b_hi + ko), idesc_cat, accumulate);
+                umma_f16(d, make_desc(a_lo), make_desc(b_hi + ko), idesc_one, 1);
               }
               accumulate = 1;
             }
@@ -189,23 +193,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
       };
       for (int it = 0; it <= my_tiles; ++it) {
         if (it < my_tiles) {                                   // M1(it): conv1 of tile it
-          const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-          mbar_wait(&a1free[buf], ph ^ 1);
+          mbar_wait(a1free, (it & 1) ^ 1);                     // E1(it-1) has drained acc1
           mbar_wait(xfull, it & 1);
           tc_fence_after();
-          conv(tmem_base + buf * 2 * ACC, smem_u32(xwin), Cfg::XPLANE, p.dil);
+          conv(tmem_base, smem_u32(xwin), Cfg::XPLANE, p.dil);
           umma_commit(xempty);
-          umma_commit(&a1full[buf]);
+          umma_commit(a1full);
         }
         if (it > 0) {                                          // M2(it-1): conv2 of the previous tile
           const int jt = it - 1;
-          const uint32_t buf = jt & 1, ph = (jt >> 1) & 1;
-          mbar_wait(&a2free[buf], ph ^ 1);
+          mbar_wait(a2free, (jt & 1) ^ 1);                     // E2(jt-1) has drained acc2
           mbar_wait(midfull, jt & 1);
           tc_fence_after();
-          conv(tmem_base + buf * 2 * ACC + ACC, smem_u32(mid), Cfg::MPLANE, 1);
+          conv(tmem_base + ACC, smem_u32(mid), Cfg::MPLANE, 1);
           umma_commit(midfree);
-          umma_commit(&a2full[buf]);
+          umma_commit(a2full);
         }
       }
     }
@@ -226,20 +228,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
         const int t = tt * R_OUT - h2 + m;                     // time step of this a1 row
         const int len = p.lens ? min(p.lens[b], p.L) : p.L;
         const bool valid = t >= 0 && t < len;                  // outside the utterance a1 is the conv's ZERO padding
-        const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-        mbar_wait(&a1full[buf], ph);
+        mbar_wait(a1full, it & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + buf * 2 * ACC + ms * C + cc * 32 + lane_addr;
+        const uint32_t taddr = tmem_base + ms * 2 * C + cc * 32 + lane_addr;
         uint32_t hi2[16], lo2[16];
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
-          uint32_t r[16];
-          tmem_ld16(taddr + ci * 16, r);
+          uint32_t r[16], rb[16];
+          tmem_ld16(taddr + ci * 16, r);                       // a_hi*w_hi + a_lo*w_hi
+          tmem_ld16(taddr + C + ci * 16, rb);                  // a_hi*w_lo
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
             const float2 s0 = sb1[cc * 32 + ci * 16 + j], s1 = sb1[cc * 32 + ci * 16 + j + 1];
-            float v0 = fmaf(__uint_as_float(r[j]), s0.x, s0.y), v1 = fmaf(__uint_as_float(r[j + 1]), s1.x, s1.y);
+            float v0 = fmaf(__uint_as_float(r[j]) + __uint_as_float(rb[j]), s0.x, s0.y);
+            float v1 = fmaf(__uint_as_float(r[j + 1]) + __uint_as_float(rb[j + 1]), s1.x, s1.y);
             v0 = v0 < 0.f ? v0 * p.slope : v0;
             v1 = v1 < 0.f ? v1 * p.slope : v1;
             split16x2(valid ? v0 : 0.f, valid ? v1 : 0.f, hi2[ci * 8 + (j >> 1)], lo2[ci * 8 + (j >> 1)]);
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a1free[buf]);              // accumulator drained
+        if (lane == 0) mbar_arrive(a1free);                    // accumulator drained
         mbar_wait(midfree, (it & 1) ^ 1);                      // conv2 of the previous tile has read the a1 tiles
         // K-major SWIZZLE_64B tile [128 rows][32 ch]: 16-byte piece c16 of row r lives at piece c16 ^ ((r >> 1) & 3)
         uint8_t* mt = mid + (cc * 2) * Cfg::MPLANE + ms * A_TILE_BYTES;
@@ -276,15 +279,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
           prefetch_l2(p.x16 + rowoff);
           prefetch_l2(p.x16 + plane + rowoff);
         }
-        const uint32_t buf = jt & 1, ph = (jt >> 1) & 1;
-        mbar_wait(&a2full[buf], ph);
+        mbar_wait(a2full, jt & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + buf * 2 * ACC + ACC + ms * C + cc * 32 + lane_addr;
+        const uint32_t taddr = tmem_base + ACC + ms * 2 * C + cc * 32 + lane_addr;
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
           const int c0 = ci * 16;
-          uint32_t r[16];
+          uint32_t r[16], rb[16];
           tmem_ld16(taddr + c0, r);
+          tmem_ld16(taddr + C + c0, rb);
           uint32_t rh[8], rl[8];
           float old[16];
           if (o_in) {
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
           if (ci == 1) {                                       // last TMEM read of this warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a2free[buf]);
+            if (lane == 0) mbar_arrive(a2free);
           }
           float v[16];
 #pragma unroll
@@ -320,8 +323,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
             float a0 = ah.x + al.x, a1 = ah.y + al.y;          // stored lrelu(x): invert
             a0 = a0 < 0.f ? a0 * p.inv_slope : a0;
             a1 = a1 < 0.f ? a1 * p.inv_slope : a1;
-            v[j] = o_valid ? fmaf(__uint_as_float(r[j]), s0.x, s0.y) + a0 : 0.f;
-            v[j + 1] = o_valid ? fmaf(__uint_as_float(r[j + 1]), s1.x, s1.y) + a1 : 0.f;
+            v[j] = o_valid ? fmaf(__uint_as_float(r[j]) + __uint_as_float(rb[j]), s0.x, s0.y) + a0 : 0.f;
+            v[j + 1] = o_valid ? fmaf(__uint_as_float(r[j + 1]) + __uint_as_float(rb[j + 1]), s1.x, s1.y) + a1 : 0.f;
           }
           if (p.out16 && o_in) {
             uint32_t h2_[8], l2_[8];
