@@ -507,16 +507,16 @@ def run_e2e(args, desc, rank, world, local):
                 flat = torch.cat(a16) if a16 else torch.zeros(0, dtype=torch.int16, device=dev)
                 sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
                 dist.all_gather(sizes, torch.tensor([flat.numel()], dtype=torch.int64, device=dev))
-                if rank == 0:
-                    bufs = [torch.empty(int(sz), dtype=torch.int16, device=dev) for sz in sizes[1:]]
+                host = None
+                if rank == 0:      # NCCL has no int16: the audio travels as bytes
+                    bufs = [torch.empty(2 * int(sz), dtype=torch.uint8, device=dev) for sz in sizes[1:]]
                     ops = [dist.P2POp(dist.irecv, b_, r + 1) for r, b_ in enumerate(bufs) if b_.numel()]
                     for w_ in (dist.batch_isend_irecv(ops) if ops else []):
                         w_.wait()
-                    host = [flat.cpu()] + [b_.cpu() for b_ in bufs]
+                    host = [flat.cpu()] + [b_.view(torch.int16).cpu() for b_ in bufs]
                 elif flat.numel():
-                    for w_ in dist.batch_isend_irecv([dist.P2POp(dist.isend, flat, 0)]):
+                    for w_ in dist.batch_isend_irecv([dist.P2POp(dist.isend, flat.view(torch.uint8), 0)]):
                         w_.wait()
-                    host = None
             else:
                 host = [torch.cat(a16).cpu()]
             return n_samples, host
