@@ -582,6 +582,13 @@ def run_ragged(args, desc, rank, world, local):
         big = synthetic_logmel(1, max(frames), seed=77)[0]
         mels = [torch.roll(big, shifts=37 * i, dims=1)[:, :f].contiguous().to(dev) for i, f in enumerate(frames)]
     total = sum(voc.out_len(f) for f in frames)
+    emu = args.emulate_world if (world == 1 and args.emulate_world > 1) else 0
+    if emu:                                   # one rank's share of an `emu`-GPU run, no communication
+        shard = cube.lpt_shard(frames, emu)[0]
+        mels = [mels[i] for i in shard]
+        frames = [frames[i] for i in shard]
+        total = sum(voc.out_len(f) for f in frames)
+        n_utt = len(frames)
 
     stats = {}
 
@@ -624,7 +631,9 @@ def run_ragged(args, desc, rank, world, local):
             "metric": "audio samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic; " + wdesc, "rtf": value / SR,
-            "config": {"workload": desc, "utterances": n_utt, "total_seconds_of_audio": total / SR, "frames_min_max": [min(frames), max(frames)],
+            "config": {"workload": desc + (f" [rank 0's LPT shard of an emulated {emu}-GPU run, on one GPU]" if emu else ""), "utterances": n_utt,
+                       "total_seconds_of_audio": total / SR, "frames_min_max": [min(frames), max(frames)], "emulated_world": emu or None,
+                       "batches": [len(b_) for b_ in cube.api.make_batches(sorted(range(len(frames)), key=lambda i: -frames[i]), frames, 64, 64 * 1400)],
                        "parallelism": f"dp{world}: LPT shards (max/mean load {max(loads) / (sum(loads) / world):.3f}), NCCL p2p scatter of mel / gather of audio",
                        "l2": "per-step working set >> 126 MB L2"},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
@@ -649,6 +658,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug)")
     ap.add_argument("--frames", type=int, default=0, help="override frames per utterance (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-world", type=int, default=0,
+                    help="ragged workload on ONE GPU: vocode only rank 0's LPT shard of a world of this size (what one rank of an N-GPU run computes)")
     args = ap.parse_args()
     arch, B, F, desc = WORKLOADS[args.workload]
     B = args.batch or B

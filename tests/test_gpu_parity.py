@@ -695,6 +695,8 @@ def test_mel_copy_synthesis_chain(dev, neb):
     pytest.param({"CUBE_TC_WIN": "0"}, "hifigan and tcgen05 and not full_size and not loudness", id="hifigan_no_window"),
     pytest.param({"CUBE_TC_RBFUSE": "0"}, "hifigan and tcgen05 and not loudness", id="hifigan_unfused_resblock_steps"),
     pytest.param({"CUBE_TC_FP8": "0"}, "student and tcgen05", id="student_pair_fp16x3"),
+    pytest.param({"CUBE_TC_AONCE": "1"}, "student and tcgen05", id="student_pair_a_once"),
+    pytest.param({"CUBE_TC_AONCE": "1", "CUBE_TC_FP8": "0"}, "student and tcgen05 and not 862", id="student_pair_a_once_fp16x3"),
     pytest.param({"CUBE_TC_FP8": "0", "CUBE_TC_PAIR": "0"}, "student and tcgen05 and not 862", id="student_single_cta_fp16x3"),
     pytest.param({"CUBE_TC_PAIR": "0"}, "student and tcgen05 and not full_length", id="student_single_cta_fp8"),
 ])

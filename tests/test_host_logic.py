@@ -162,6 +162,16 @@ def test_make_batches_and_padding():
     nf = [10, 9, 9, 4, 3, 1]
     assert make_batches(range(6), nf, 4) == [[0, 1, 2, 3], [4, 5]]
     assert make_batches(range(6), nf, 64, max_frames=25) == [[0, 1], [2, 3], [4, 5]]
+    # padding-aware: an LPT shard mixes long and short utterances; a batch must not be mostly padding
+    g = torch.Generator().manual_seed(9)
+    nf2 = sorted(torch.randint(188, 1407, (32,), generator=g).tolist(), reverse=True)
+    one = make_batches(range(32), nf2, 64, max_pad_ratio=1e9)
+    assert len(one) == 1 and 32 * nf2[0] > 1.4 * sum(nf2)                       # one padded batch: > 40 % waste
+    bs = make_batches(range(32), nf2, 64)
+    assert sorted(i for b in bs for i in b) == list(range(32)) and 2 <= len(bs) <= 6
+    padded = sum(len(b) * nf2[b[0]] for b in bs)
+    assert padded <= 1.25 * sum(nf2)
+    assert all(len(b) >= 4 for b in bs[:-1])
     m = pad_mels([torch.ones(80, 3), torch.ones(80, 5)], pad_value=-5.0)
     assert m.shape == (2, 80, 5) and float(m[0, 0, 4]) == -5.0 and float(m[1, 0, 4]) == 1.0
 

@@ -1462,8 +1462,11 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
         const bool stats = block_stats_on();                             // instrumented build: wait cycles of CTA 0
         if (stats) bp.stats = block_stats_buf();
         // the PAIR x Q8 x STATS instantiations of the one kernel template
+        static int aonce = -1;      // pair tiling with the A chunk staged once for both n-tiles (tc_block.cuh, AONCE); CUBE_TC_AONCE=0/1
+        if (aonce < 0) { const char* e = getenv("CUBE_TC_AONCE"); aonce = (e && e[0] == '1') ? 1 : 0; }
+        const bool use_aonce = pairv == 1 && aonce == 1 && !stats;
         auto launch = [&](auto kernel, bool pair) -> int {
-          const size_t smem = pair ? tc::PAIR_SMEM : tc::BLK_SMEM;
+          const size_t smem = use_aonce ? tc::AONCE_SMEM : (pair ? tc::PAIR_SMEM : tc::BLK_SMEM);
           static std::map<std::pair<const void*, int>, bool> attr_done;
           const auto key = std::make_pair((const void*)kernel, h->device);
           if (!attr_done[key]) {
@@ -1491,7 +1494,9 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
           return 0;
         };
         int lrc;
-        if (pairv == 1) {
+        if (use_aonce) {
+          lrc = q8 ? launch(tc::tc_block_kernel<true, true, false, true>, true) : launch(tc::tc_block_kernel<true, false, false, true>, true);
+        } else if (pairv == 1) {
           if (stats) lrc = q8 ? launch(tc::tc_block_kernel<true, true, true>, true) : launch(tc::tc_block_kernel<true, false, true>, true);
           else lrc = q8 ? launch(tc::tc_block_kernel<true, true, false>, true) : launch(tc::tc_block_kernel<true, false, false>, true);
         } else {

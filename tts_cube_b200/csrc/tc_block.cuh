@@ -29,10 +29,16 @@ namespace tc {
 //                 accumulator / o-buffer hand-shakes: the peer's epilogue warps arrive remotely (relaxed, cluster scope -
 //                 the release form compiles to MEMBAR.ALL.GPU) on the leader's barriers, tcgen05.commit multicasts
 //                 completions to both CTAs.
-template <bool PAIR> struct BlkCfg {
-  static constexpr int NST = PAIR ? 4 : 3;                                            // ring stages
+//   AONCE (PAIR only): a GEMM1 stage carries the A chunk ONCE and the weight halves of BOTH 256-column n-tiles (48 KB, 3 stages);
+//                 the two n-tiles accumulate side by side in the two TMEM regions.  A is no longer loaded twice per tile
+//                 (L2 -> shared memory bytes per tile 1.09 -> 0.85 MB, 47 instead of 64 B per MMA cycle, 3 k instead of 2 k cycles of
+//                 latency covered by the ring); the price is that both regions are busy until the gate epilogues have drained
+//                 them, so the next tile's GEMM1 cannot start under this tile's epilogues.
+template <bool PAIR, bool AONCE = false> struct BlkCfg {
+  static_assert(PAIR || !AONCE, "AONCE is a mode of the CTA-pair tiling");
+  static constexpr int NST = AONCE ? 3 : (PAIR ? 4 : 3);                              // ring stages
   static constexpr int B_BYTES = (PAIR ? 128 : 256) * BK * 2;                         // this CTA's weight rows, one fp16 plane
-  static constexpr int STG = 2 * A_TILE_BYTES + 2 * B_BYTES;                          // 32 / 48 KB
+  static constexpr int STG = 2 * A_TILE_BYTES + (AONCE ? 4 : 2) * B_BYTES;            // 32 / 48 KB
   static constexpr int O_BYTES = 2 * 4 * A_TILE_BYTES;                                // 4 chunks x (hi, lo) = 64 KB
   static constexpr int SMEM = NST * STG + O_BYTES + 1024 + 512 + 768 * 8;
   static constexpr int TILE_ROWS = PAIR ? 2 * BM : BM;
@@ -40,6 +46,7 @@ template <bool PAIR> struct BlkCfg {
 constexpr int BLK_O_BYTES = BlkCfg<false>::O_BYTES;
 constexpr int BLK_SMEM = BlkCfg<false>::SMEM;
 constexpr int PAIR_SMEM = BlkCfg<true>::SMEM;
+constexpr int AONCE_SMEM = BlkCfg<true, true>::SMEM;
 static_assert(BK == 32, "tc_block_kernel is written for 32-channel K chunks (SWIZZLE_64B)");
 
 struct BlockParams {
@@ -111,15 +118,17 @@ __device__ __forceinline__ void blk_commit(uint64_t* bar) {
 // signal the peer CTA's barrier).
 // STATS: instrumented build (CUBE_BLOCK_STATS=1): CTA 0's cycles per barrier wait.
 // 18 warps: the SM sub-partitions hold 5,5,4,4 of them, so 16384/5 -> 96 registers per thread is the hardware cap
-template <bool PAIR, bool Q8, bool STATS = false>
+template <bool PAIR, bool Q8, bool STATS = false, bool AONCE = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_constant__ BlockParams p) {
   long long st_acc[STATS ? 8 : 1] = {0};
   const long long st_begin = STATS ? clock64() : 0;
   (void)st_acc; (void)st_begin;
   constexpr int BN = 256;
-  constexpr int B_BYTES = BlkCfg<PAIR>::B_BYTES;   // this CTA's weight rows (all 256, or its HALF of the pair's tile), one fp16 plane
-  constexpr int NST = BlkCfg<PAIR>::NST;
-  constexpr int STG = BlkCfg<PAIR>::STG;
+  constexpr int B_BYTES = BlkCfg<PAIR, AONCE>::B_BYTES;   // this CTA's weight rows (all 256, or its HALF of the pair's tile), one fp16 plane
+  constexpr int NST = BlkCfg<PAIR, AONCE>::NST;
+  constexpr int STG = BlkCfg<PAIR, AONCE>::STG;
+  constexpr int NPASS = AONCE ? 1 : 2;             // GEMM1 passes over the K chunks (one per n-tile, or one for both)
+  constexpr int NTP = AONCE ? 2 : 1;               // n-tiles per pass
   constexpr int TILE_ROWS = BlkCfg<PAIR>::TILE_ROWS;
   constexpr int NARR = PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS;      // epilogue warps that arrive on the leader's hand-shake barriers
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;               // 0 = leader: issues the MMAs
@@ -128,7 +137,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* o_smem = smem + NST * STG;      // [4 chunks][hi 8 KB | lo 8 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(o_smem + BlkCfg<PAIR>::O_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(o_smem + BlkCfg<PAIR, AONCE>::O_BYTES);
   uint64_t* full = bars;                       // [4] this CTA's stage has landed
   uint64_t* empty = bars + NST;                // [4] (commit multicast: both CTAs)
   uint64_t* pfull = bars + 2 * NST;            // [4] leader only: the PEER's stage has landed (relayed by its MMA warp)
@@ -180,8 +189,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int tt = tile % p.t_tiles, b = tile / p.t_tiles;
         const int t0 = tt * TILE_ROWS + (int)crank * BM;       // this CTA's 128 rows of the tile
-        for (int nt = 0; nt < 2; ++nt) {                       // GEMM1, one 256-column n-tile at a time
-          const __half* wt = p.W1 + (size_t)nt * nch1 * 2 * (BN * BK);
+        for (int pass = 0; pass < NPASS; ++pass) {             // GEMM1: one 256-column n-tile per pass, or (AONCE) both in one pass
           int chunk = 0;
           for (int tap = 0; tap <= p.taps; ++tap) {            // tap == p.taps: the conditioning segment
             const bool cond = tap == p.taps;
@@ -195,21 +203,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
               mbar_expect_tx(&full[st], STG);
               const CUtensorMap* tm = cond ? &p.tmC : &p.tmH;
               tma_load_3d_bar(sb, tm, fbar, cc * BK, row, b);
-              if constexpr (Q8) {
-                // a_hi fp16 (8 KB) | e4m3(a_hi) (4 KB) | e5m2(16 a_lo) (4 KB); one 32 KB weight image
+              if constexpr (Q8) {   // a_hi fp16 (8 KB) | e4m3(a_hi) (4 KB) | e5m2(16 a_lo) (4 KB)
                 const CUtensorMap* tm8 = cond ? &p.tmC8 : &p.tmH8;
                 tma_load_3d_bar(sb + A_TILE_BYTES, tm8, fbar, cc * BK, row, b);
                 tma_load_3d_bar(sb + A_TILE_BYTES + A_TILE_BYTES / 2, tm8, fbar, cc * BK, row, p.B + b);
-                // rows [128 crank, +128) of each of the three sub-images of the 32 KB chunk image
-                const uint8_t* wq = p.W1q + ((size_t)nt * nch1 + chunk) * 32768;
-                bulk_load_bar(sb + 2 * A_TILE_BYTES, wq + crank * B_BYTES, B_BYTES, fbar);
-                bulk_load_bar(sb + 2 * A_TILE_BYTES + B_BYTES, wq + 16384 + crank * (B_BYTES / 2), B_BYTES / 2, fbar);
-                bulk_load_bar(sb + 2 * A_TILE_BYTES + B_BYTES + B_BYTES / 2, wq + 24576 + crank * (B_BYTES / 2), B_BYTES / 2, fbar);
               } else {
                 tma_load_3d_bar(sb + A_TILE_BYTES, tm, fbar, cc * BK, row, p.B + b);
-                const __half* wc = wt + (size_t)chunk * 2 * (BN * BK) + (size_t)crank * (BN / 2) * BK /* crank = 0 without PAIR */;   // this CTA's 128 weight rows
-                bulk_load_bar(sb + 2 * A_TILE_BYTES, wc, B_BYTES, fbar);
-                bulk_load_bar(sb + 2 * A_TILE_BYTES + B_BYTES, wc + BN * BK, B_BYTES, fbar);
+              }
+#pragma unroll
+              for (int k = 0; k < NTP; ++k) {                  // this CTA's weight rows of the n-tile(s) of this pass
+                const int nt = AONCE ? k : pass;
+                uint8_t* wb = sb + 2 * A_TILE_BYTES + k * 2 * B_BYTES;
+                if constexpr (Q8) {
+                  // rows [128 crank, +128) of each of the three sub-images of the 32 KB chunk image
+                  const uint8_t* wq = p.W1q + ((size_t)nt * nch1 + chunk) * 32768;
+                  bulk_load_bar(wb, wq + crank * B_BYTES, B_BYTES, fbar);
+                  bulk_load_bar(wb + B_BYTES, wq + 16384 + crank * (B_BYTES / 2), B_BYTES / 2, fbar);
+                  bulk_load_bar(wb + B_BYTES + B_BYTES / 2, wq + 24576 + crank * (B_BYTES / 2), B_BYTES / 2, fbar);
+                } else {
+                  const __half* wc = p.W1 + ((size_t)nt * nch1 + chunk) * 2 * (BN * BK) + (size_t)crank * (BN / 2) * BK /* crank = 0 without PAIR */;
+                  bulk_load_bar(wb, wc, B_BYTES, fbar);
+                  bulk_load_bar(wb + B_BYTES, wc + BN * BK, B_BYTES, fbar);
+                }
               }
             }
           }
@@ -237,7 +252,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
       // peer CTA: it issues no MMA; this thread relays "my stage has landed" to the leader
       uint32_t it = 0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step)
-        for (int n = 2 * nch1 + 8; n > 0; --n, ++it) {
+        for (int n = NPASS * nch1 + 8; n > 0; --n, ++it) {
           const int st = it % NST;
           mbar_wait(&full[st], (it / NST) & 1);
           mbar_arrive_remote(&pfull[st], 0);
@@ -249,13 +264,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
       uint32_t ofull_ph = 0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step, ++titer) {
         const int r0 = titer & 1, r1 = r0 ^ 1;      // region roles of this tile
-        for (int nt = 0; nt < 2; ++nt) {
-          const int rg = nt == 0 ? r0 : r1;
-          // the region must have been drained by its previous user (first use of each region: passes at once)
-          BLK_WAIT(&acc_free[rg], (free_ph[rg] & 1) ^ 1, nt);
-          ++free_ph[rg];
+        for (int pass = 0; pass < NPASS; ++pass) {
+          // the region(s) must have been drained by their previous user (first use of each region: passes at once)
+#pragma unroll
+          for (int k = 0; k < NTP; ++k) {
+            const int rg = (AONCE ? k : pass) == 0 ? r0 : r1;
+            BLK_WAIT(&acc_free[rg], (free_ph[rg] & 1) ^ 1, AONCE ? k : pass);
+            ++free_ph[rg];
+          }
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + rg * BN;
           uint32_t accumulate = 0;
           for (int tap = 0; tap <= p.taps; ++tap) {
             const bool cond = tap == p.taps;
@@ -266,32 +283,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
               if constexpr (PAIR) BLK_WAIT(&pfull[st], (it / NST) & 1, 2);
               tc_fence_after();
               const uint32_t a_hi = smem_u32(smem + st * STG), a_lo = a_hi + A_TILE_BYTES;
-              const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + B_BYTES;
               const int ksteps = (cond && cc == ncc - 1) ? p.c_last_ksteps : (BK / 16);
-              if constexpr (Q8) {
-                // hi*hi in fp16 (K = 16 per MMA), then the two 2^-11-weight corrections as ONE 8-bit MMA each (K = 32):
-                // e4m3(a_hi) x e4m3(w_lo)  and  e5m2(16 a_lo) x e4m3(w_hi / 16)  -> 4 MMAs per chunk instead of 6
-                for (int ks = 0; ks < ksteps; ++ks) {
-                  blk_mma_f16<PAIR>(d_tmem, make_desc(a_hi + ks * 32), make_desc(b_hi + ks * 32), idesc, accumulate);
-                  accumulate = 1;
-                }
-                const uint32_t a8_hi = a_hi + A_TILE_BYTES, a8_lo = a8_hi + A_TILE_BYTES / 2;
-                const uint32_t b8_lo = b_hi + B_BYTES, b8_hi = b8_lo + B_BYTES / 2;
-                blk_mma_f8<PAIR>(d_tmem, make_desc32(a8_hi), make_desc32(b8_lo), make_idesc_f8(BN, TILE_ROWS, 0), 1);
-                blk_mma_f8<PAIR>(d_tmem, make_desc32(a8_lo), make_desc32(b8_hi), make_idesc_f8(BN, TILE_ROWS, 1), 1);
-              } else {
-                for (int ks = 0; ks < ksteps; ++ks) {
-                  const uint32_t ko = ks * 32;
-                  blk_mma_f16<PAIR>(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
-                  blk_mma_f16<PAIR>(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
-                  blk_mma_f16<PAIR>(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
-                  accumulate = 1;
+#pragma unroll
+              for (int k = 0; k < NTP; ++k) {
+                const int rg = (AONCE ? k : pass) == 0 ? r0 : r1;
+                const uint32_t d_tmem = tmem_base + rg * BN;
+                const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES + k * 2 * B_BYTES, b_lo = b_hi + B_BYTES;
+                uint32_t acc_k = accumulate;
+                if constexpr (Q8) {
+                  // hi*hi in fp16 (K = 16 per MMA), then the two 2^-11-weight corrections as ONE 8-bit MMA each (K = 32):
+                  // e4m3(a_hi) x e4m3(w_lo)  and  e5m2(16 a_lo) x e4m3(w_hi / 16)  -> 4 MMAs per chunk instead of 6
+                  for (int ks = 0; ks < ksteps; ++ks) {
+                    blk_mma_f16<PAIR>(d_tmem, make_desc(a_hi + ks * 32), make_desc(b_hi + ks * 32), idesc, acc_k);
+                    acc_k = 1;
+                  }
+                  const uint32_t a8_hi = a_hi + A_TILE_BYTES, a8_lo = a8_hi + A_TILE_BYTES / 2;
+                  const uint32_t b8_lo = b_hi + B_BYTES, b8_hi = b8_lo + B_BYTES / 2;
+                  blk_mma_f8<PAIR>(d_tmem, make_desc32(a8_hi), make_desc32(b8_lo), make_idesc_f8(BN, TILE_ROWS, 0), 1);
+                  blk_mma_f8<PAIR>(d_tmem, make_desc32(a8_lo), make_desc32(b8_hi), make_idesc_f8(BN, TILE_ROWS, 1), 1);
+                } else {
+                  for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint32_t ko = ks * 32;
+                    blk_mma_f16<PAIR>(d_tmem, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, acc_k);
+                    blk_mma_f16<PAIR>(d_tmem, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+                    blk_mma_f16<PAIR>(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                    acc_k = 1;
+                  }
                 }
               }
+              accumulate = 1;
               blk_commit<PAIR>(&empty[st]);
             }
           }
-          blk_commit<PAIR>(&acc_full[rg]);
+#pragma unroll
+          for (int k = 0; k < NTP; ++k) blk_commit<PAIR>(&acc_full[(AONCE ? k : pass) == 0 ? r0 : r1]);
         }
         // GEMM2 into r0 (drained by the gate epilogue of n-tile 0): K half kh uses the o half the epilogue staged
         {
