@@ -50,7 +50,7 @@ BLOCK_FLOPS = GATE_FLOPS + 2.0 * (256 * 256)               # + res/skip 1x1 256 
 BLOCK_BYTES = 4.0 * (128 + 80 + 128 + 128 + 128)           # read h, c_up, skip; write h', skip (fp32 equivalents)
 HIFI_FLOPS_PER_SAMPLE = 1022.2e3                           # SURVEY 8(d), neb-noft rates
 HIFI_BYTES_PER_SAMPLE = 9021.0
-FUSED_TRAFFIC = 3.23e9                                     # dram read + write of one tc_block_kernel launch (ncu --set full)
+FUSED_TRAFFIC = 2.83e9 + 2.21e9                            # dram read + write of one default block-kernel launch (ncu --set full, round 2)
 PWN_FLOPS_PER_SAMPLE = 25.63e6
 PWN_BYTES_PER_SAMPLE = 103609.0
 
@@ -780,17 +780,16 @@ def main():
         flops_launch = (BLOCK_FLOPS if fused else GATE_FLOPS) * samples_per_step
         ach = flops_launch * nlaunch / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else None
         roof = {"kernel": "conv_tile_kernel<8,8,8,1> EPI_GATE (gated dilated conv k3 128->2x256 + conditioning 1x1 80->2x256, fp32 FFMA2)" if math == 0
-                else ("tc::tc_block_pair_kernel (whole residual block on a CTA pair: gated dilated conv + conditioning 1x1 -> o kept in smem "
+                else ("tc::tc_block_kernel<PAIR, Q8> (whole residual block on a CTA pair: gated dilated conv + conditioning 1x1 -> o kept in smem "
                       "-> res/skip 1x1; tcgen05 cta_group::2 UMMA 256x256, hi*hi in fp16 + two 8-bit correction passes in GEMM1, TMA taps; "
-                      "CUBE_TC_PAIR=0 / CUBE_TC_FP8=0 select the single-CTA / three-fp16-pass variants)" if fused else
+                      "CUBE_TC_PAIR=0 / CUBE_TC_FP8=0 / CUBE_TC_AONCE select the single-CTA / three-fp16-pass / A-once variants)" if fused else
                       "tc::tc_conv_kernel TC_EPI_GATE (same layer on tcgen05: UMMA 128x256x16 f16, split-fp16 x3, TMA taps)"),
                 "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                 "frac": (ach / pk["tf_sust"]) if ach else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, round 1
-                # (profiles/r1_ncu_full_tc_conv.md: 1.52 GB + 1.79 GB); only valid for the default geometry
-                # ncu capture of the single-CTA three-pass kernel (the pair kernel moves the same DRAM bytes: same tensors)
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the default kernel (CTA pair + 8-bit correction
+                # passes), ncu --set full, round 2; only valid for the default geometry and switches
                 "traffic": (FUSED_TRAFFIC if fused else 3.31e9) if (math == 1 and B == 8 and F == 862) else None,
-                "traffic_source": ("profiles/r1_ncu_full_tc_block.md (ncu --set full, one tc_block_kernel launch, single-CTA variant)" if fused else
+                "traffic_source": ("profiles/r2_ncu_full_tc_block_pair.md (ncu --set full, one launch of the default block kernel: 2.83 GB read + 2.21 GB written)" if fused else
                                    "profiles/r1_ncu_full_tc_conv.md (ncu --set full, gate launch)"),
                 "launches_per_step": nlaunch, "avg_launch_ms": dom_ms / max(1, nlaunch),
                 "algorithmic_flops_per_launch": flops_launch, "algorithmic_bytes_per_launch": (BLOCK_BYTES if fused else GATE_BYTES) * samples_per_step,

@@ -160,18 +160,25 @@ def test_lpt_shard_properties():
 def test_make_batches_and_padding():
     from tts_cube_b200.api import make_batches, pad_mels
     nf = [10, 9, 9, 4, 3, 1]
-    assert make_batches(range(6), nf, 4) == [[0, 1, 2, 3], [4, 5]]
-    assert make_batches(range(6), nf, 64, max_frames=25) == [[0, 1], [2, 3], [4, 5]]
+    assert make_batches(range(6), nf, 4, batch_overhead_frames=0) == [[0], [1, 2], [3], [4], [5]]    # padding only: equal lengths pair up
+    one = make_batches(range(6), nf, 64, batch_overhead_frames=10 ** 6)
+    assert one == [[0, 1, 2, 3, 4, 5]]                                          # launches dominate: one batch
+    capped = make_batches(range(6), nf, 64, max_frames=25, batch_overhead_frames=10 ** 6)
+    assert all(len(b) * nf[b[0]] <= 25 for b in capped) and sorted(i for b in capped for i in b) == list(range(6))
+    assert make_batches([], nf, 4) == []
     # padding-aware: an LPT shard mixes long and short utterances; a batch must not be mostly padding
     g = torch.Generator().manual_seed(9)
     nf2 = sorted(torch.randint(188, 1407, (32,), generator=g).tolist(), reverse=True)
-    one = make_batches(range(32), nf2, 64, max_pad_ratio=1e9)
-    assert len(one) == 1 and 32 * nf2[0] > 1.4 * sum(nf2)                       # one padded batch: > 40 % waste
+    assert 32 * nf2[0] > 1.4 * sum(nf2)                                          # one padded batch would be > 40 % waste
     bs = make_batches(range(32), nf2, 64)
     assert sorted(i for b in bs for i in b) == list(range(32)) and 2 <= len(bs) <= 6
+    assert all(b == list(range(b[0], b[-1] + 1)) for b in bs)                    # consecutive runs of the sorted list
     padded = sum(len(b) * nf2[b[0]] for b in bs)
     assert padded <= 1.25 * sum(nf2)
-    assert all(len(b) >= 4 for b in bs[:-1])
+    # optimal for its cost model: no single cut or merge improves it
+    cost = lambda bb: sum(len(b) * nf2[b[0]] + 1600 for b in bb)
+    for k in range(len(bs) - 1):
+        assert cost(bs) <= cost(bs[:k] + [bs[k] + bs[k + 1]] + bs[k + 2:])
     m = pad_mels([torch.ones(80, 3), torch.ones(80, 5)], pad_value=-5.0)
     assert m.shape == (2, 80, 5) and float(m[0, 0, 4]) == -5.0 and float(m[1, 0, 4]) == 1.0
 
