@@ -29,7 +29,12 @@ typedef void* cube_stream_t; /* cudaStream_t */
 enum cube_voc_arch {
   CUBE_VOC_HIFIGAN = 0,     /* hifigan/models.py:Generator (Path H)                               */
   CUBE_VOC_PWN_STUDENT = 1, /* ClariNet IAF student + UpsampleNet2 (Path C), weights-only in ref  */
-  CUBE_VOC_WAVERNN = 2      /* cube/networks/modules.py:WaveRNN (Path W), autoregressive          */
+  CUBE_VOC_WAVERNN = 2,     /* cube/networks/modules.py:WaveRNN (Path W), autoregressive          */
+  CUBE_VOC_UPSAMPLENET = 3  /* cube/networks/modules.py:317-343 UpsampleNet: 3 x (Conv1d k + tanh), then per scale s a
+                             * weight-normed ConvTranspose1d(2s, stride s, padding s/2) + tanh.  Config: num_mels = in_channels,
+                             * res_channels = out_channels, kernel_size (odd), n_upsample / upsample_scales (even scales).
+                             * cube_voc_forward(mel [B, in, F]) writes `wav` as [B, out_channels, F * prod(scales)];
+                             * cube_voc_out_len = F * prod(scales) */
 };
 
 /* 'beta' (cube/networks/loss.py:69-106, selectable at modules.py:436-437) is NOT supported: its sample() draws from

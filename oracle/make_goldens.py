@@ -12,6 +12,7 @@ imported from where they lie and only their numerical outputs are stored.
                        (weights NOT stored - staged by oracle/stage_weights.py), F=24
   heads.npz            cube/networks/loss.py MULAW/RAW/MOL/Gaussian encode/decode/sample
   upsample2.npz        cube/networks/modules.py UpsampleNet2/R/I (+ teacher upsample weights)
+  upsamplenet.npz      cube/networks/modules.py:317-343 UpsampleNet (3 conv+tanh, weight-normed transposed convs), seeded weights stored
   mel_hifigan.npz      hifigan/meldataset.py:mel_spectrogram (librosa stubbed with torchaudio's Slaney filter bank)
   clarinet_regress.npz NOT reference-derived (no forward code in the reference): regression
                        snapshot of oracle/clarinet_ref.py with the shipped checkpoints
@@ -148,7 +149,7 @@ def main():
     print("clarinet_regress", tuple(xs.shape), "std", float(xs.std()), "peak", float(xs.abs().max()))
 
 
-_ONLY = {"--inc-only", "--wavernn", "--mel"} & set(sys.argv)      # no flag: regenerate everything
+_ONLY = {"--inc-only", "--wavernn", "--mel", "--upsamplenet"} & set(sys.argv)      # no flag: regenerate everything
 
 if __name__ == "__main__" and not _ONLY:
     main()
@@ -256,3 +257,26 @@ def mel_goldens():
 
 if __name__ == "__main__" and (not _ONLY or "--mel" in _ONLY):
     mel_goldens()
+
+
+def upsamplenet_golden():
+    """tests/golden/upsamplenet.npz: the UNMODIFIED reference UpsampleNet (cube/networks/modules.py:317-343), default-initialised
+    under torch.manual_seed(77), scales [2, 2, 4], 80 -> 24 channels; weights, input and output stored."""
+    sys.path.insert(0, REF)
+    from cube.networks import modules as ref_mod     # reference
+    from oracle import wavernn_ref as R
+    torch.manual_seed(77)
+    scales = [2, 2, 4]
+    m = ref_mod.UpsampleNet(upsample_scales=scales, in_channels=80, out_channels=24, kernel_size=3).eval()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    c = torch.rand(2, 80, 9, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    with torch.no_grad():
+        y = m(c)
+    assert float((R.upsamplenet_forward(sd, c, scales) - y).abs().max()) == 0.0
+    np.savez_compressed(os.path.join(OUT, "upsamplenet.npz"), c=c.numpy(), y=y.numpy(), scales=np.array(scales), in_channels=80,
+                        out_channels=24, kernel_size=3, **{"w:" + k: v.numpy() for k, v in sd.items()})
+    print("upsamplenet", tuple(y.shape), float(y.abs().max()))
+
+
+if __name__ == "__main__" and (not _ONLY or "--upsamplenet" in _ONLY):
+    upsamplenet_golden()

@@ -132,3 +132,19 @@ def random_state_dict(H: int = 64, n_layers: int = 2, use_lowres: bool = True, S
     lin("_preoutput.linear_layer", 256, H)
     lin("_output.linear_layer", S, 256)
     return sd
+
+
+@torch.no_grad()
+def upsamplenet_forward(sd: Dict[str, torch.Tensor], c: torch.Tensor, scales, kernel_size: int = 3) -> torch.Tensor:
+    """Reference ``UpsampleNet.forward`` (cube/networks/modules.py:317-343) restated functionally: three
+    ``tanh(Conv1d(k, padding=k // 2))`` (ModuleList indices 0, 2, 4), then per scale s
+    ``tanh(ConvTranspose1d(2 s, stride=s, padding=s // 2))`` with weight-norm (g over dim 0 of the [C_in, C_out, K] weight).
+    ``sd`` holds the reference module's own state_dict.  Pinned by tests/golden/upsamplenet.npz (reference-run)."""
+    x = c.to(torch.float32)
+    for i in range(3):
+        x = torch.tanh(F.conv1d(x, sd[f"_conv.{2 * i}.weight"], sd[f"_conv.{2 * i}.bias"], padding=kernel_size // 2))
+    for n, s in enumerate(scales):
+        p = f"_upsample_conv.{2 * n}."
+        w = torch._weight_norm(sd[p + "weight_v"], sd[p + "weight_g"], 0) if p + "weight_v" in sd else sd[p + "weight"]
+        x = torch.tanh(F.conv_transpose1d(x, w, sd[p + "bias"], stride=s, padding=s // 2))
+    return x

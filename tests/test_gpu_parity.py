@@ -617,6 +617,46 @@ def test_cubegan_inference_through_the_drop_in(dev):
     assert float((wavs[0].cpu() - torch.from_numpy(d["wav"])[0, 0]).abs().max()) <= TOL
 
 
+def test_upsamplenet_golden_and_oracle(dev):
+    """Reference UpsampleNet (cube/networks/modules.py:317-343): reference-run golden, then a wider / longer / ragged case
+    (kernel 5, scales [4, 2], livelier weights) against the oracle."""
+    import tts_cube_b200 as cube
+    from oracle import wavernn_ref as R
+    d = load_golden("upsamplenet.npz")
+    sd = golden_weights(d)
+    scales = [int(s) for s in d["scales"]]
+    m = cube.UpsampleNet(scales, int(d["in_channels"]), int(d["out_channels"]), int(d["kernel_size"])).to(dev)
+    m.load_state_dict(sd)
+    y = m(torch.from_numpy(d["c"]).to(dev)).cpu().numpy()
+    assert y.shape == d["y"].shape
+    assert float(np.abs(y - d["y"]).max()) <= 1e-6
+    g = torch.Generator().manual_seed(3)
+    Cin, Co, K, sc = 40, 96, 5, [4, 2]
+    sd2 = {}
+    ic = Cin
+    for i in range(3):
+        sd2[f"_conv.{2 * i}.weight"] = torch.randn(Co, ic, K, generator=g) * (1.5 / (ic * K) ** 0.5)
+        sd2[f"_conv.{2 * i}.bias"] = torch.randn(Co, generator=g) * 0.1
+        ic = Co
+    for n, s_ in enumerate(sc):
+        sd2[f"_upsample_conv.{2 * n}.weight_v"] = torch.randn(Co, Co, 2 * s_, generator=g) * 0.1
+        sd2[f"_upsample_conv.{2 * n}.weight_g"] = 0.5 + torch.rand(Co, 1, 1, generator=g)
+        sd2[f"_upsample_conv.{2 * n}.bias"] = torch.randn(Co, generator=g) * 0.1
+    m2 = cube.UpsampleNet(sc, Cin, Co, K).to(dev)
+    m2.load_state_dict(sd2)
+    c = torch.rand(3, Cin, 37, generator=g) * 2 - 1
+    frames = [37, 5, 20]
+    y2 = m2(c.to(dev), n_frames=frames).cpu()
+    assert y2.shape == (3, Co, 37 * 8)
+    for b, f in enumerate(frames):
+        ref = R.upsamplenet_forward(sd2, c[b:b + 1, :, :f], sc, K)[0]
+        assert float(ref.abs().max()) > 0.3
+        assert float((y2[b, :, : f * 8] - ref).abs().max()) <= 2e-5, b
+        assert f == 37 or float(y2[b, :, f * 8:].abs().max()) == 0.0
+    with pytest.raises(cube.CubeVocError):
+        cube.UpsampleNet([3], 8, 8, 3).to(dev).forward(torch.zeros(1, 8, 4, device=dev))      # odd scale: rejected
+
+
 # ------------------------------------------------ mel front-end ------------------------------------------------
 MEL_TOL = 2e-4      # log-mel units (fp32 DFT by direct summation vs torch's FFT; measured ~1e-5)
 

@@ -183,3 +183,13 @@ def test_teacher_generate_is_consistent_with_teacher_forcing():
     want = ml[:, 0, :-1] + 0.8 * eps[:, :-1] * torch.exp(ml[:, 1, :-1])
     assert float((x[:, 0, 1:] - want).abs().max()) <= 1e-5
     assert float(x.abs().max()) > 1e-3
+
+
+def test_upsamplenet_oracle_matches_reference():
+    """cube/networks/modules.py:317-343: the restatement equals the reference-run golden bit for bit"""
+    from oracle import wavernn_ref as R
+    d = load_golden("upsamplenet.npz")
+    sd = golden_weights(d)
+    y = R.upsamplenet_forward(sd, torch.from_numpy(d["c"]), [int(s) for s in d["scales"]], int(d["kernel_size"]))
+    assert y.shape == d["y"].shape == (2, 24, 9 * 16)
+    assert float((y - torch.from_numpy(d["y"])).abs().max()) == 0.0

@@ -13,7 +13,7 @@ from ._lib import CubeVocError, build_info, LIB_PATH  # noqa: F401
 from .generator import CubeGenerator, install_into_cubegan  # noqa: F401
 from .clarinet import ParallelWaveNetVocoder  # noqa: F401
 from .heads import MULAWOutput, RAWOutput, MOLOutput, GaussianOutput  # noqa: F401
-from .wavernn import WaveRNNVocoder, CubenetVocoder  # noqa: F401
+from .wavernn import WaveRNNVocoder, CubenetVocoder, UpsampleNet  # noqa: F401
 from .api import synthesize, lpt_shard, cubegan_inference_batch  # noqa: F401
 from .mel import MelSpectrogram, MelVocoder, mel_spectrogram, slaney_mel_basis  # noqa: F401
 

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcube_vocoder.so")
 
 MAX_UPS, MAX_RBK, MAX_DIL, MAX_FLOWS = 8, 8, 8, 8
-ARCH_HIFIGAN, ARCH_PWN_STUDENT, ARCH_WAVERNN = 0, 1, 2
+ARCH_HIFIGAN, ARCH_PWN_STUDENT, ARCH_WAVERNN, ARCH_UPSAMPLENET = 0, 1, 2, 3
 HEADS = {"mol": 0, "gm": 1, "mulaw": 2, "raw": 3}
 MATH_FP32_SIMT, MATH_TC_SPLIT16 = 0, 1
 

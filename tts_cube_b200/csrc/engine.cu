@@ -142,6 +142,8 @@ struct cube_voc {
     float *wpre = nullptr, *bpre = nullptr, *wout = nullptr, *bout = nullptr;
     int S = 0, ic = 0;
   } wr;
+  // UpsampleNet (cube/networks/modules.py:317-343)
+  struct UpNet { PackedConv conv[3]; std::vector<PackedConv> up; std::vector<int> J; } upnet;
   // last-forward geometry (for get_cond)
   int last_B = 0; int64_t last_T = 0;
 };
@@ -1757,6 +1759,72 @@ static int forward_wavernn(cube_voc* h, const float* mel, const float* x_low, co
   return lx.err;
 }
 
+// ------------------------------------------------------------------------------------------------
+// UpsampleNet (cube/networks/modules.py:317-343): finalize + forward on the fp32 kernels
+// ------------------------------------------------------------------------------------------------
+static int finalize_upsamplenet(cube_voc* h) {
+  const cube_voc_config& c = h->cfg;
+  const int Cin = c.num_mels, Co = c.res_channels, K = c.kernel_size;
+  int ic = Cin;
+  for (int i = 0; i < 3; ++i) {       // ModuleList [Conv1d, Tanh] x 3: the convs sit at indices 0, 2, 4
+    if (pack_conv1d(h, "_conv." + std::to_string(2 * i), Co, ic, K, &h->upnet.conv[i])) return 1;
+    ic = Co;
+  }
+  h->upnet.up.resize(c.n_upsample);
+  h->upnet.J.resize(c.n_upsample);
+  for (int n = 0; n < c.n_upsample; ++n) {
+    const int s_ = c.upsample_scales[n];
+    if (pack_convT(h, "_upsample_conv." + std::to_string(2 * n), Co, Co, 2 * s_, s_, &h->upnet.up[n], &h->upnet.J[n])) return 1;
+  }
+  return 0;
+}
+
+static int forward_upsamplenet(cube_voc* h, const float* mel, const int32_t* n_frames, float* out, int B, int64_t Fmax, cudaStream_t st) {
+  const cube_voc_config& c = h->cfg;
+  const int Cin = c.num_mels, Co = c.res_channels, K = c.kernel_size;
+  int64_t T64 = Fmax;
+  for (int n = 0; n < c.n_upsample; ++n) T64 *= c.upsample_scales[n];
+  if (T64 > 0x7fffffffLL / 2) return fail("utterance too long");
+  if (upload_lens(h, n_frames, B, Fmax, c.n_upsample + 1, st)) return 1;
+  float *a, *b2;
+  const size_t big = (size_t)B * Co * (size_t)std::max<int64_t>(Fmax, T64 / c.upsample_scales[c.n_upsample - 1]);
+  if (ws_get(h, "un_a", big, &a) || ws_get(h, "un_b", big, &b2)) return 1;
+  Launcher lx{h, st};
+  const float* src = mel;
+  int ic = Cin;
+  const int F = (int)Fmax;
+  float* pp[2] = {a, b2};
+  for (int i = 0; i < 3; ++i) {       // c = tanh(conv_k(c)), "same" padding k/2
+    lx.begin("upnet_conv");
+    ConvP p = make_conv(h->upnet.conv[i]);
+    p.nseg = 1;
+    p.seg[0] = make_seg(src, (long long)ic * F, ic, F, K, 1, -(K / 2), PRE_NONE, 0.f, h->d_lens);
+    p.Q = F; p.L_out = F; p.out_lens = h->d_lens; p.post = POST_TANH;
+    p.out = pp[i & 1]; p.out_bstride = (long long)Co * F;
+    lx.conv(p, B);
+    lx.end();
+    src = pp[i & 1]; ic = Co;
+  }
+  int Lin = F, which = 1;             // the last conv wrote pp[0] (i = 2): the next output goes to pp[1]
+  for (int n = 0; n < c.n_upsample; ++n) {   // c = tanh(convT_{2s, stride s, padding s/2}(c))
+    const int s_ = c.upsample_scales[n], pad = s_ / 2, J = h->upnet.J[n], Lo = Lin * s_;
+    const bool last = n == c.n_upsample - 1;
+    lx.begin("upnet_up");
+    ConvP p = make_conv(h->upnet.up[n]);
+    p.nseg = 1;
+    p.seg[0] = make_seg(src, (long long)Co * Lin, Co, Lin, J, 1, -(J - 1), PRE_NONE, 0.f, h->d_lens + (size_t)n * B);
+    p.nphase = s_; p.ostride = s_;
+    for (int r = 0; r < s_; ++r) p.ooff[r] = r - pad;
+    p.Q = (Lo - 1 + pad) / s_ + 1;
+    p.L_out = Lo; p.out_lens = h->d_lens + (size_t)(n + 1) * B; p.post = POST_TANH;
+    p.out = last ? out : pp[which]; p.out_bstride = (long long)Co * Lo;
+    lx.conv(p, B);
+    lx.end();
+    src = pp[which]; which ^= 1; Lin = Lo;
+  }
+  return lx.err;
+}
+
 static int ensure_device(cube_voc* h) {
   CU_TRY(cudaSetDevice(h->device));
   return 0;
@@ -1815,7 +1883,7 @@ int cube_voc_create(cube_voc_t** out, const cube_voc_config* cfg, int device) {
   if (e != cudaSuccess || ndev == 0)
     return fail("no CUDA device: libcube_vocoder has no CPU path (%s)", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
   if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
-  if (cfg->arch != CUBE_VOC_HIFIGAN && cfg->arch != CUBE_VOC_PWN_STUDENT && cfg->arch != CUBE_VOC_WAVERNN)
+  if (cfg->arch != CUBE_VOC_HIFIGAN && cfg->arch != CUBE_VOC_PWN_STUDENT && cfg->arch != CUBE_VOC_WAVERNN && cfg->arch != CUBE_VOC_UPSAMPLENET)
     return fail("unknown arch %d", cfg->arch);
   if (cfg->arch == CUBE_VOC_HIFIGAN) {
     if (cfg->n_ups < 1 || cfg->n_ups > CUBE_MAX_UPS) return fail("n_ups %d out of range", cfg->n_ups);
@@ -1835,6 +1903,13 @@ int cube_voc_create(cube_voc_t** out, const cube_voc_config* cfg, int device) {
     if (cfg->wrnn_size < 8 || cfg->wrnn_size > 1024 || cfg->wrnn_size % 4) return fail("WaveRNN layer_size must be a multiple of 4 in [8, 1024]");
     if (cfg->wrnn_upsample < 1 || (cfg->wrnn_use_lowres && cfg->wrnn_upsample_low < 1)) return fail("bad upsample");
     if (cfg->wrnn_head < 0 || cfg->wrnn_head > 3) return fail("unknown head");
+  } else if (cfg->arch == CUBE_VOC_UPSAMPLENET) {
+    if (cfg->n_upsample < 1 || cfg->n_upsample > 4) return fail("n_upsample out of range");
+    if (cfg->num_mels < 1 || cfg->res_channels < 1) return fail("UpsampleNet needs num_mels (in_channels) and res_channels (out_channels)");
+    if (cfg->kernel_size < 1 || cfg->kernel_size % 2 != 1 || cfg->kernel_size > 31) return fail("UpsampleNet kernel_size must be odd (got %d)", cfg->kernel_size);
+    for (int i = 0; i < cfg->n_upsample; ++i)
+      if (cfg->upsample_scales[i] < 2 || cfg->upsample_scales[i] > 8 || cfg->upsample_scales[i] % 2)
+        return fail("UpsampleNet scales must be even and in [2, 8] (got %d): odd scales change the length law", cfg->upsample_scales[i]);
   } else {
     if (cfg->n_flows < 1 || cfg->n_flows > CUBE_MAX_FLOWS) return fail("n_flows out of range");
     if (cfg->n_upsample < 1 || cfg->n_upsample > 4) return fail("n_upsample out of range");
@@ -1873,7 +1948,9 @@ int cube_voc_finalize(cube_voc_t* h) {
   if (h->finalized) return 0;
   if (ensure_device(h)) return 1;
   if (tables_ready()) return 1;
-  int rc = h->cfg.arch == CUBE_VOC_HIFIGAN ? finalize_hifigan(h) : (h->cfg.arch == CUBE_VOC_WAVERNN ? finalize_wavernn(h) : finalize_student(h));
+  int rc = h->cfg.arch == CUBE_VOC_HIFIGAN ? finalize_hifigan(h)
+         : h->cfg.arch == CUBE_VOC_WAVERNN ? finalize_wavernn(h)
+         : h->cfg.arch == CUBE_VOC_UPSAMPLENET ? finalize_upsamplenet(h) : finalize_student(h);
   if (rc) return rc;
   h->host_w.clear();
   CU_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -1902,6 +1979,10 @@ int cube_voc_forward(cube_voc_t* h, const float* mel, const int32_t* n_frames, c
   cudaStream_t st = (cudaStream_t)stream;
   if (h->cfg.arch == CUBE_VOC_WAVERNN) return fail("use cube_wavernn_forward for a WaveRNN handle");
   if (h->cfg.arch == CUBE_VOC_HIFIGAN) return forward_hifigan(h, mel, n_frames, wav, wav_i16, B, Fmax, st);
+  if (h->cfg.arch == CUBE_VOC_UPSAMPLENET) {
+    if (wav_i16) return fail("UpsampleNet has no int16 output");
+    return forward_upsamplenet(h, mel, n_frames, wav, B, Fmax, st);
+  }
   return forward_student(h, mel, n_frames, noise, wav, wav_i16, B, Fmax, st);
 }
 
@@ -1919,6 +2000,7 @@ int cube_voc_forward_host(cube_voc_t* h, const float* mel, const int32_t* n_fram
   if (!mel || (!wav && !wav_i16)) return fail("null mel / no output buffer");
   if (B < 1 || Fmax < 1) return fail("empty batch");
   if (h->cfg.arch == CUBE_VOC_WAVERNN) return fail("use cube_wavernn_forward for a WaveRNN handle");
+  if (h->cfg.arch == CUBE_VOC_UPSAMPLENET) return fail("the host-buffer call is defined for the waveform vocoders; use cube_voc_forward for UpsampleNet");
   if (h->cfg.arch == CUBE_VOC_PWN_STUDENT && !noise) return fail("the IAF student needs `noise` (z ~ N(0,1), [B,1,T])");
   if (ensure_device(h)) return 1;
   const int64_t T = cube_voc_out_len(h, Fmax);

@@ -183,3 +183,88 @@ class CubenetVocoder(torch.nn.Module):
         m, xl = fold_batch(mel, x_lr, self._upsample_low, num_batches=20)
         x_hr = unfold_batch(self._wavernn_hr.inference(m, xl, draws_hr), self._upsample)
         return x_lr.unsqueeze(2).cpu().numpy(), x_hr.cpu()
+
+
+class UpsampleNet(torch.nn.Module):
+    """``cube/networks/modules.py:317-343``: 3 x (Conv1d(k) + tanh), then per scale s a weight-normed
+    ConvTranspose1d(2s, stride s, padding s // 2) + tanh - the learned mel upsampler of the WaveRNN family (the reference
+    keeps it as an alternative to ``UpsampleNetR`` / ``UpsampleNetI``, modules.py:411).  Same constructor arguments, same
+    state-dict keys (``_conv.{0,2,4}.*``, ``_upsample_conv.{0,2,..}.weight_g/weight_v/bias``), ``forward(c [B, C, T']) ->
+    [B, out_channels, T' * prod(scales)]``; ``n_frames`` masks a right-padded batch.  Even scales only (an odd scale
+    changes the reference's own length law to T' * s + 1)."""
+
+    def __init__(self, upsample_scales=(2, 2, 4), in_channels=80, out_channels=80, kernel_size=3):
+        super().__init__()
+        lib()
+        cfg = VocConfig()
+        cfg.arch = _lib.ARCH_UPSAMPLENET
+        cfg.num_mels, cfg.res_channels, cfg.kernel_size = int(in_channels), int(out_channels), int(kernel_size)
+        scales = [int(s) for s in upsample_scales]
+        if not 1 <= len(scales) <= 4:
+            raise _lib.CubeVocError("UpsampleNet takes 1..4 upsample scales")
+        cfg.n_upsample = len(scales)
+        for i, s in enumerate(scales):
+            cfg.upsample_scales[i] = s
+        self._cfg, self._scales, self._out = cfg, scales, int(out_channels)
+        self._sd: Dict[str, torch.Tensor] = {}
+        self._handle: Optional[_Handle] = None
+        self.register_buffer("_device_tracker", torch.zeros(1), persistent=False)
+
+    @property
+    def device(self) -> torch.device:
+        return self._device_tracker.device
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):  # noqa: D102
+        self._sd = {k: v.detach().to("cpu", torch.float32).clone() for k, v in state_dict.items()}
+        if self._handle is not None:
+            self._handle.close()
+            self._handle = None
+        return torch.nn.modules.module._IncompatibleKeys([], [])
+
+    def state_dict(self, *a, **k):  # noqa: D102
+        return dict(self._sd)
+
+    def _apply(self, fn, *a, **k):
+        before = self._device_tracker.device
+        r = super()._apply(fn, *a, **k)
+        if self._device_tracker.device != before and self._handle is not None:
+            self._handle.close()
+            self._handle = None
+        return r
+
+    def _ensure(self) -> _Handle:
+        if self._handle is None:
+            dev = self.device
+            if dev.type != "cuda":
+                raise _lib.CubeVocError("UpsampleNet must be moved to a CUDA device; there is no CPU path")
+            if not self._sd:
+                raise _lib.CubeVocError("load_state_dict() must be called before forward()")
+            dev = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+            hd = _Handle(self._cfg, dev)
+            hd.load(self._sd)
+            hd.finalize()
+            self._handle = hd
+        return self._handle
+
+    def out_len(self, n_frames: int) -> int:
+        t = int(n_frames)
+        for s in self._scales:
+            t *= s
+        return t
+
+    def forward(self, c: torch.Tensor, n_frames=None) -> torch.Tensor:
+        import ctypes as C
+        hd = self._ensure()
+        if c.device.type != "cuda" or c.dtype != torch.float32 or c.dim() != 3:
+            raise _lib.CubeVocError(f"c must be a CUDA float32 [B, C, T'] tensor, got {c.dtype} {tuple(c.shape)} on {c.device}")
+        hd._check_shapes(c, n_frames)
+        if c.device != hd.device:
+            raise _lib.CubeVocError(f"c lives on {c.device} but this module's weights live on {hd.device}")
+        c = c.contiguous()
+        B, _, F = c.shape
+        out = torch.empty(B, self._out, self.out_len(F), device=c.device, dtype=torch.float32)
+        nf = (C.c_int32 * B)(*[int(v) for v in n_frames]) if n_frames is not None else None
+        with torch.cuda.device(c.device):
+            _lib.check(lib().cube_voc_forward(hd.ptr, C.c_void_p(c.data_ptr()), nf, None, C.c_void_p(out.data_ptr()), None, B, F,
+                                              C.c_void_p(torch.cuda.current_stream(c.device).cuda_stream)))
+        return out
