@@ -305,9 +305,24 @@ WORKER = textwrap.dedent("""
             alone = H.generator_forward(sd, cfg, mels[i][None])[0, 0]
             assert res[i].shape == alone.shape, (res[i].shape, alone.shape)
             assert float((res[i] - alone).abs().max()) <= 1e-6, i
-        print("OK")
     else:
         assert res is None
+    # the noise path (IAF student): z blocks travel with the mel blocks, utterance by utterance
+    hop = 4
+    voc3 = lambda mel, z, frames: mel.mean(1, keepdim=True).repeat_interleave(hop, dim=2) + z
+    lens3 = [6, 11, 3, 8, 8, 2, 9]
+    mels3 = [torch.full((80, f), float(i + 1)) for i, f in enumerate(lens3)] if rank == 0 else None
+    zs3 = [torch.arange(hop * f, dtype=torch.float32) * 1e-3 + i for i, f in enumerate(lens3)] if rank == 0 else None
+    stats = {{}}
+    res3 = synthesize(None, mels3, zs=zs3, device=torch.device("cpu"), max_batch=3, vocode=voc3, out_len=lambda f: hop * f, stats=stats)
+    if rank == 0:
+        for i, f in enumerate(lens3):
+            want = float(i + 1) + zs3[i]
+            assert res3[i].shape == want.shape and float((res3[i] - want).abs().max()) <= 1e-6, i
+        assert stats["scatter_bytes"] > 0 and stats["gather_bytes"] > 0 and len(stats["batches_per_rank"]) == 2
+        print("OK")
+    else:
+        assert res3 is None
     dist.barrier()
 """)
 

@@ -1458,7 +1458,10 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
         bp.lens = lens_T; bp.skip = sk; bp.skip_set = (i == 0); bp.scale = rs;
         bp.skip16 = (i == nb - 1) ? s16 : nullptr;
         const bool q8 = fp8 && fl.has_tc_front && fl.tc_gate[i].Wimg8;
-        if (q8) { bp.tmH8 = tm_h8; bp.tmC8 = tm_c8; bp.W1q = fl.tc_gate[i].Wimg8; bp.h8_out = h8b; }
+        if (q8) { bp.tmH8 = tm_h8; bp.tmC8 = tm_c8; bp.W1q = fl.tc_gate[i].Wimg8; bp.h8_out = h8b; bp.h8_in = h8; bp.c8_in = c8; }
+        static int pfn = -1;        // L2 prefetch of the next tile's A rows by the epilogue warps; CUBE_TC_PREFETCH=0/1
+        if (pfn < 0) { const char* e = getenv("CUBE_TC_PREFETCH"); pfn = (e && e[0] == '1') ? 1 : 0; }
+        bp.prefetch_next = pfn; bp.c_in16 = c16; bp.c_ch = CI;
         static int pairv = -1;      // CTA-pair (cta_group::2) tiling of the block kernel; CUBE_TC_PAIR=0: one CTA per tile
         if (pairv < 0) { const char* e = getenv("CUBE_TC_PAIR"); pairv = (e && e[0] == '0') ? 0 : 1; }
         const bool stats = block_stats_on();                             // instrumented build: wait cycles of CTA 0

@@ -68,6 +68,15 @@ struct BlockParams {
   CUtensorMap tmH8, tmC8;        // uint8 planes [2B][T][C]: plane 0 = e4m3(a_hi), plane 1 = e5m2(16 a_lo); boxes 32 B x 128 rows
   const uint8_t* W1q;            // gate images [2 n-tiles][nch1][32 KB]: w_hi fp16 (SW64) | e4m3(w_lo) | e4m3(w_hi/16) (SW32)
   uint8_t* h8_out;               // 8-bit planes of the block OUTPUT (the next block's A operand)
+  // ---- L2 prefetch of the NEXT tile's A rows by the (mostly waiting) epilogue warps: the residual stream and the conditioning
+  // do not fit in L2 between launches, so a ring stage's A boxes come from DRAM while its weights come from L2; pulled into
+  // L2 a tile ahead (plain prefetch.global.L2 through the LSU: nothing queues in the TMA engine, unlike the bulk prefetch
+  // that was tried in round 1), both arrive with L2 latency.  0 = off.
+  int prefetch_next;
+  const __half* c_in16;          // conditioning planes [2][B][T][c_ch] (what tmC maps)
+  const uint8_t* h8_in;          // Q8: 8-bit planes of the block input (what tmH8 maps), conditioning (tmC8)
+  const uint8_t* c8_in;
+  int c_ch;                      // channels of the conditioning planes (80)
   unsigned long long* stats;     // STATS build only: wait-cycle counters of CTA 0 (CUBE_BLOCK_STATS=1), 24 slots
 };
 
@@ -368,6 +377,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
       const int r0 = titer & 1, r1 = r0 ^ 1;
       const int len = p.lens ? min(p.lens[b], p.T) : p.T;
       const bool in_range = t < p.T, valid = t < len;
+      if (p.prefetch_next && tile + tile_step < total_tiles) {
+        // the A rows of this CTA's NEXT tile -> L2: per tap 128 rows x (h: 2 planes; 256 B fp16 / 128 B 8-bit per row),
+        // one 128-byte line per thread and step; the conditioning rows of the tile likewise
+        const int ntile = tile + tile_step;
+        const int ntt = ntile % p.t_tiles, nb = ntile / p.t_tiles;
+        const int nt0 = ntt * TILE_ROWS + (int)crank * BM;
+        const int e = (int)threadIdx.x - 64;               // 0..511
+        const int rr = e & 127, part = e >> 7;             // row of the box, which quarter of the row's bytes
+        const size_t hplane = (size_t)p.B * p.T * 128;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int row = nt0 + p.off0 + tap * p.dil + rr;
+          if (row >= 0 && row < p.T) {
+            const size_t ro = (size_t)nb * p.T + row;
+            if constexpr (Q8) {      // fp16 hi plane: 2 lines; 8-bit planes: 1 line each
+              if (part < 2) prefetch_l2(p.h_in16 + ro * 128 + part * 64);
+              else prefetch_l2(p.h8_in + (size_t)(part - 2) * hplane + ro * 128);
+            } else {                 // fp16 hi and lo planes: 2 lines each
+              prefetch_l2(p.h_in16 + (size_t)(part >> 1) * hplane + ro * 128 + (part & 1) * 64);
+            }
+          }
+        }
+        const int crow = nt0 + rr;
+        if (crow < p.T && p.c_in16) {
+          const size_t ro = (size_t)nb * p.T + crow;
+          const size_t cplane = (size_t)p.B * p.T * p.c_ch;
+          if constexpr (Q8) {
+            if (part < 2) prefetch_l2(p.c_in16 + ro * p.c_ch + part * 64);                       // 160 B of fp16: two lines
+            else if (p.c8_in) prefetch_l2(p.c8_in + (size_t)(part - 2) * cplane + ro * p.c_ch);  // 80 B per 8-bit plane
+          } else {
+            prefetch_l2(p.c_in16 + (size_t)(part >> 1) * cplane + ro * p.c_ch + (part & 1) * 64);
+          }
+        }
+      }
       // a flow's last block reads the running skip total: pull this warp's slice into L2 while the MMAs run
       if (in_range && p.skip16 && !p.skip_set && (lane & 7) == 0) {
         const float* s0 = p.skip + ((size_t)b * 128 + grp * 32) * p.T + t;
