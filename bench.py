@@ -236,21 +236,32 @@ def cpu_sample_shape(rate, F, hop, seconds):
     return batch, frames
 
 
-def cpu_calibrated_sample(arch, weights, threads, F, hop, seconds, max_rounds=3):
-    """(batch, frames, samples/s) of a CPU sample that takes about `seconds`.  The rate of torch's CPU convs depends on
-    the clip length (short clips live in cache, long ones stream from DRAM), so a short probe is only a first guess:
-    the sample is re-sized from its OWN measured rate until it lands within [0.6, 1.5] x the budget, growing by at
-    most 4x per round - no round can overshoot the budget by more than the rate drop between two sizes."""
-    rate, _, _ = cpu_oracle_rate(arch, weights, 12 if arch == "student" else 200, threads)      # ~0.5 s probe
-    target = min(seconds, 1.0)
-    cb, frames = cpu_sample_shape(rate, F, hop, target)
-    for _ in range(max_rounds):
-        rate, n, dt = cpu_oracle_rate(arch, weights, frames, threads, cb)
-        if 0.6 * seconds <= dt <= 1.5 * seconds:
-            break
-        target = min(seconds, 4.0 * dt) if dt < seconds else seconds
-        cb, frames = cpu_sample_shape(rate, F, hop, target)
-    return cb, frames, rate
+# CPU sample per step: FIXED shapes, never grown.  The rate of torch's CPU convs depends strongly on the clip length (short
+# clips live in cache, long ones stream from DRAM), so sizing a sample from a probe of another length overshoots by multiples
+# (round 1 lost its GPU box that way, the first round-2 attempt took 6 min); a fixed shape has a known cost, and the only
+# adjustment allowed is to SHRINK it once when the measured time says the run would not fit its wall-clock budget
+# (a smaller clip is never slower per sample, so shrinking cannot overshoot).
+# (batch, frames).  The student's CPU rate still falls with the clip length at these sizes (16 host threads: ~7 k samples/s at
+# 128 frames, 5.7 k at 256, 5.3 k at a full 862-frame utterance, which takes 40 s), so the short per-step sample of the reference
+# arm slightly FLATTERS the CPU; the one-off cpu_baseline of the product arm uses a longer clip.
+CPU_SAMPLE = {"step": {"student": (1, 128), "hifigan": (2, 919)},          # --impl reference: one of these per step
+              "baseline": {"student": (1, 256), "hifigan": (4, 919)}}      # product arm, cpu_baseline leg: measured once
+
+
+def cpu_fit_sample(arch, weights, threads, F, n_calls, wall_budget_s, kind="step"):
+    """(batch, frames) for `n_calls` timed calls within `wall_budget_s`: the fixed shape, shrunk once if one measured call
+    says the run would not fit.  The measuring call doubles as a warm-up."""
+    cb, frames = CPU_SAMPLE[kind][arch]
+    frames = min(frames, F)
+    _, n, dt = cpu_oracle_rate(arch, weights, frames, threads, cb)
+    if dt * n_calls > wall_budget_s:
+        scale = wall_budget_s / (dt * n_calls)
+        if cb > 1 and scale * cb >= 1.0:
+            cb = max(1, int(cb * scale))
+        else:
+            frames = max(8, int(frames * cb * scale))
+            cb = 1
+    return cb, frames
 
 
 def torch_cuda_baseline(arch, weights, mel, z, steps=2):
@@ -300,9 +311,8 @@ def run_reference(args, arch, B, F, desc, rank, world):
     weights, wdesc = load_weights(arch)
     threads = best_cpu_threads(arch, weights)
     n_calls = max(1, args.steps + args.warmup)
-    budget = min(5.0, 75.0 / n_calls)                                   # seconds of CPU per step
     hop = 256 if arch == "student" else 240
-    cb, frames, _ = cpu_calibrated_sample(arch, weights, threads, F, hop, budget)
+    cb, frames = cpu_fit_sample(arch, weights, threads, F, n_calls, wall_budget_s=100.0)
     for _ in range(args.warmup):
         cpu_oracle_rate(arch, weights, frames, threads, cb)
     tot_s, tot_t = 0, 0.0
@@ -829,7 +839,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only (the N>1 lines carry null)
         threads = best_cpu_threads(arch, weights)     # cached in /tmp by the reference arm when that ran first
         hop = 256 if arch == "student" else 240
-        cb, frames, _ = cpu_calibrated_sample(arch, weights, threads, F, hop, 10.0)
+        cb, frames = cpu_fit_sample(arch, weights, threads, F, n_calls=2, wall_budget_s=40.0, kind="baseline")   # = the warm-up call
         r2, n, dt = cpu_oracle_rate(arch, weights, frames, threads, cb)
         cpu = {"value": r2, "unit": "samples/s", "cores": threads, "kind": "port",
                "sample": f"B={cb} x {frames} frames ({n} samples, {dt:.1f} s of CPU) of the same synthetic workload; oracle port, torch CPU fp32, "
