@@ -323,6 +323,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return d;
 }
 
+// descriptor of the tile `byte_off` bytes further on (byte_off a multiple of 16, the sum still inside shared memory): only the
+// 14-bit start-address field changes, and it cannot carry out of the low word.  ONE integer add - which matters: a single thread
+// issues every MMA, and building each descriptor from its address (shift, mask, ors, 64-bit pack) costs ~75 cycles per MMA
+// (tools/umma_microbench.cu: 74.9 cycles with per-MMA descriptor arithmetic, 50.9 with descriptors ready, for MMAs whose math is
+// 16-64 cycles) - the narrow HiFi-GAN MMAs were issue-bound by exactly that.
+__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off) {
+  return (d & 0xFFFFFFFF00000000ull) | (uint64_t)((uint32_t)d + (byte_off >> 4));
+}
+
 // instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n
 __host__ __device__ constexpr uint32_t make_idesc(int n, int m = BM) {
   return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -584,21 +593,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
                 const int sbi = ib % SB;
                 mbar_wait(&fullB[sbi], (ib / SB) & 1);
                 tc_fence_after();
-                const uint32_t b_hi = smem_u32(smem + SA * A_SLOT + sbi * B_SLOT), b_lo = b_hi + B_SLOT / 2;
+                const uint32_t b_hi = smem_u32(smem + SA * A_SLOT + sbi * B_SLOT);
                 const uint32_t a_tap = a_base + (uint32_t)(tap * sg.dil) * ROW_BYTES;   // row offset of this tap in the window
+                // descriptors once per (chunk, tap); every MMA below adds a compile-time offset (desc_add)
+                const uint64_t dah = make_desc(a_tap), dal = make_desc(a_tap + A_LO_OFF), dbh = make_desc(b_hi), dbl = make_desc(b_hi + B_SLOT / 2);
                 for (int ks = 0; ks < ksteps; ++ks) {
                   const uint32_t ko = ks * 32;
 #pragma unroll
                   for (int ms = 0; ms < MSUB; ++ms) {
-                    const uint32_t a_hi = a_tap + ms * A_TILE_BYTES, a_lo = a_hi + A_LO_OFF;
+                    const uint32_t ao = ms * A_TILE_BYTES + ko;
                     const uint32_t d = d_tmem + ms * ACCW;
                     if constexpr (CAT) {     // [w_hi | w_lo] is one K-major tile of 2 TN rows (the lo image follows the hi image)
-                      umma_f16(d, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc_cat, accumulate);
-                      umma_f16(d, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                      umma_f16(d, desc_add(dah, ao), desc_add(dbh, ko), idesc_cat, accumulate);
+                      umma_f16(d, desc_add(dal, ao), desc_add(dbh, ko), idesc, 1);
                     } else {
-                      umma_f16(d, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, accumulate);
-                      umma_f16(d, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
-                      umma_f16(d, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, 1);
+                      umma_f16(d, desc_add(dah, ao), desc_add(dbh, ko), idesc, accumulate);
+                      umma_f16(d, desc_add(dah, ao), desc_add(dbl, ko), idesc, 1);
+                      umma_f16(d, desc_add(dal, ao), desc_add(dbh, ko), idesc, 1);
                     }
                   }
                   accumulate = 1;

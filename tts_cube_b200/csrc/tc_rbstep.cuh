@@ -176,18 +176,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
             const uint32_t b_hi = smem_u32(wring + s * Cfg::WIMG);      // [w_hi: C rows][w_lo: C rows], one K-major tile of 2C rows
             const uint32_t a_hi0 = a_base + (uint32_t)(cc * 2) * plane_bytes + (uint32_t)(tap * tap_rows) * ROW_BYTES;
             const uint32_t a_lo0 = a_hi0 + plane_bytes;
+            // three descriptors per (tap, chunk); every MMA below adds a compile-time offset: the issuing thread's instruction
+            // stream, not the tensor core, bounded these narrow MMAs (tc_conv.cuh: desc_add)
+            const uint64_t dah = make_desc(a_hi0), dal = make_desc(a_lo0), dbh = make_desc(b_hi);
 #pragma unroll
             for (int ks = 0; ks < BK / 16; ++ks) {
-              const uint32_t ko = ks * 32;
 #pragma unroll
               for (int ms = 0; ms < NSUB; ++ms) {
-                const uint32_t a_hi = a_hi0 + ms * A_TILE_BYTES + ko, a_lo = a_lo0 + ms * A_TILE_BYTES + ko;
+                const uint32_t ao = ms * A_TILE_BYTES + ks * 32;
                 const uint32_t d = d_tmem + ms * 2 * C;
-                umma_f16(d, make_desc(a_hi), make_desc(b_hi + ko), idesc_cat, accumulate);
-                umma_f16(d, make_desc(a_lo), make_desc(b_hi + ko), idesc_one, 1);
+                umma_f16(d, desc_add(dah, ao), desc_add(dbh, ks * 32), idesc_cat, ks == 0 ? accumulate : 1u);
+                umma_f16(d, desc_add(dal, ao), desc_add(dbh, ks * 32), idesc_one, 1);
               }
-              accumulate = 1;
             }
+            accumulate = 1;
             umma_commit(&wempty[s]);
           }
       };
