@@ -1036,7 +1036,7 @@ static int launch_rbstep(cube_voc* h, tc::RbParams& rp, cudaStream_t st) {
   rp.t_tiles = (rp.L + r_out - 1) / r_out;
   const long long tiles = (long long)rp.t_tiles * rp.B;
   const int grid = (int)std::min<long long>(tiles, h->sm_count);
-  tc::tc_rbstep_kernel<C, NSUB><<<grid, tc::NUM_THREADS, Cfg::SMEM, st>>>(rp);
+  tc::tc_rbstep_kernel<C, NSUB><<<grid, tc::RB_THREADS, Cfg::SMEM, st>>>(rp);
   return 0;
 }
 

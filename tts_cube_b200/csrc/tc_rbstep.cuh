@@ -69,8 +69,14 @@ struct RbParams {
   __half* out16b;             // TC_ACC_ADD_DIV: lrelu((acc + x') / acc_div) planes = the next stage's input
 };
 
+// 19 warps: TMA producer, MMA issuer A, 16 epilogue warps, MMA issuer B.  TWO issuing warps, each with half of the sub-tiles:
+// a narrow MMA occupies the tensor core for 40-50 cycles (tools/umma_microbench.cu) but costs its issuing thread 50-75 (descriptor
+// adds, the ELECT / UTCHMMA / branch sequence, a barrier wait and a commit per tap), so one thread cannot keep the pipe fed.
+constexpr int RB_THREADS = NUM_THREADS + 32;
+constexpr int RB_ISSUERS = 2;
+
 template <int C, int NSUB>
-__global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_constant__ RbParams p) {
+__global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_constant__ RbParams p) {
   using Cfg = RbCfg<C, NSUB>;
   constexpr int NCH = Cfg::NCH, NBOX = Cfg::NBOX, WS = Cfg::WS, ACC = Cfg::ACC;
   extern __shared__ uint8_t smem_raw[];
@@ -103,15 +109,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmX);
-    mbar_init(xfull, 1); mbar_init(xempty, 1);
-    for (int s = 0; s < WS; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-    mbar_init(a1full, 1); mbar_init(a1free, NUM_EPI_WARPS);
-    mbar_init(a2full, 1); mbar_init(a2free, NUM_EPI_WARPS);
-    mbar_init(midfull, NUM_EPI_WARPS); mbar_init(midfree, 1);
+    mbar_init(xfull, 1); mbar_init(xempty, RB_ISSUERS);                 // every issuer commits what IT issued
+    for (int s = 0; s < WS; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], RB_ISSUERS); }
+    mbar_init(a1full, RB_ISSUERS); mbar_init(a1free, NUM_EPI_WARPS);
+    mbar_init(a2full, RB_ISSUERS); mbar_init(a2free, NUM_EPI_WARPS);
+    mbar_init(midfull, NUM_EPI_WARPS); mbar_init(midfree, RB_ISSUERS);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
-  for (int i = threadIdx.x; i < C; i += NUM_THREADS) {
+  for (int i = threadIdx.x; i < C; i += RB_THREADS) {
     sb1[i] = make_float2(__ldg(p.inv1 + i), __ldg(p.bias1 + i));
     sb2[i] = make_float2(__ldg(p.inv2 + i), __ldg(p.bias2 + i));
   }
@@ -159,8 +165,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
         if (it > 0) weights(p.W2);
       }
     }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
+  } else if (warp == 1 || warp == NUM_THREADS / 32) {
+    // =========================== MMA issuers ===========================
+    // the TMEM base as a warp-uniform value: UTCHMMA takes its operands from uniform registers, and a per-thread register
+    // costs an ELECT / R2UR.BROADCAST / branch "waterfall" in front of every MMA
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    constexpr int MS_PER = NSUB / RB_ISSUERS;                  // sub-tiles per issuer
+    static_assert(NSUB % RB_ISSUERS == 0, "sub-tiles split evenly over the issuers");
+    const int ms0 = (warp == 1 ? 0 : 1) * MS_PER;
     if (lane == 0) {
       constexpr uint32_t idesc_cat = make_idesc(2 * C, BM);     // a_hi x [w_hi | w_lo]
       constexpr uint32_t idesc_one = make_idesc(C, BM);         // a_lo x w_hi
@@ -178,13 +190,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
             const uint32_t a_lo0 = a_hi0 + plane_bytes;
             // three descriptors per (tap, chunk); every MMA below adds a compile-time offset: the issuing thread's instruction
             // stream, not the tensor core, bounded these narrow MMAs (tc_conv.cuh: desc_add)
-            const uint64_t dah = make_desc(a_hi0), dal = make_desc(a_lo0), dbh = make_desc(b_hi);
+            const uint64_t dah = make_desc(a_hi0 + ms0 * A_TILE_BYTES), dal = make_desc(a_lo0 + ms0 * A_TILE_BYTES), dbh = make_desc(b_hi);
 #pragma unroll
             for (int ks = 0; ks < BK / 16; ++ks) {
 #pragma unroll
-              for (int ms = 0; ms < NSUB; ++ms) {
-                const uint32_t ao = ms * A_TILE_BYTES + ks * 32;
-                const uint32_t d = d_tmem + ms * 2 * C;
+              for (int mi = 0; mi < MS_PER; ++mi) {
+                const uint32_t ao = mi * A_TILE_BYTES + ks * 32;
+                const uint32_t d = d_tmem + mi * 2 * C;
                 umma_f16(d, desc_add(dah, ao), desc_add(dbh, ks * 32), idesc_cat, ks == 0 ? accumulate : 1u);
                 umma_f16(d, desc_add(dal, ao), desc_add(dbh, ks * 32), idesc_one, 1);
               }
@@ -198,7 +210,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
           mbar_wait(a1free, (it & 1) ^ 1);                     // E1(it-1) has drained acc1
           mbar_wait(xfull, it & 1);
           tc_fence_after();
-          conv(tmem_base, smem_u32(xwin), Cfg::XPLANE, p.dil);
+          conv(tmem_u + ms0 * 2 * C, smem_u32(xwin), Cfg::XPLANE, p.dil);
           umma_commit(xempty);
           umma_commit(a1full);
         }
@@ -207,7 +219,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_rbstep_kernel(const __grid_
           mbar_wait(a2free, (jt & 1) ^ 1);                     // E2(jt-1) has drained acc2
           mbar_wait(midfull, jt & 1);
           tc_fence_after();
-          conv(tmem_base + ACC, smem_u32(mid), Cfg::MPLANE, 1);
+          conv(tmem_u + ACC + ms0 * 2 * C, smem_u32(mid), Cfg::MPLANE, 1);
           umma_commit(midfree);
           umma_commit(a2full);
         }
