@@ -99,7 +99,12 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
   uint64_t* midfull = a2free + 1;        // [1]  epilogue (16 warps) -> MMA
   uint64_t* midfree = midfull + 1;       // [1]  MMA -> epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(midfree + 1);
-  static_assert((2 + 2 * WS + 6) * 8 + 8 <= Cfg::BAR_BYTES, "barrier block");
+  // the order of the MMA phases is decided by issuer A and FOLLOWED by issuer B (a log of 64 decisions in shared memory): both
+  // consume the same weight rings, whose slots are recycled only when BOTH have read them - two issuers taking different orders
+  // (one in conv1 waiting for ring-1 slots the other has not released, the other in conv2 waiting for ring-2 slots) deadlock
+  volatile uint32_t* ord_n = reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 384);
+  volatile uint8_t* ord = reinterpret_cast<volatile uint8_t*>(bars) + 392;
+  static_assert((2 + 2 * WS + 6) * 8 + 8 <= 384 && 392 + 64 <= Cfg::BAR_BYTES, "barrier block");
   float2* sb1 = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);   // [C] (de-scale, bias) of conv1
   float2* sb2 = sb1 + C;
 
@@ -117,6 +122,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
     mbar_init(a1full, RB_ISSUERS); mbar_init(a1free, NUM_EPI_WARPS);
     mbar_init(a2full, RB_ISSUERS); mbar_init(a2free, NUM_EPI_WARPS);
     mbar_init(midfull, NUM_EPI_WARPS); mbar_init(midfree, RB_ISSUERS);
+    *ord_n = 0u;
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -211,16 +217,32 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
       // tile i1 as soon as its x window has landed (and acc1 is drained).  A fixed "M1(i+1) then M2(i)" order made conv2 wait
       // for the NEXT tile's window load - the short k = 3 steps ran at 18 % tensor activity that way.
       int i1 = 0, i2 = 0;
+      uint32_t nd = 0;                                         // decisions made (issuer A) / followed (issuer B)
+      const bool leader = warp == 1;
       while (i2 < my_tiles) {
-        const bool can2 = i2 < i1 && mbar_test_wait(midfull, i2 & 1) && mbar_test_wait(a2free, (i2 & 1) ^ 1);
-        if (can2) {                                            // M2(i2): conv2
-          tc_fence_after();
+        int op;                                                // 1: conv2 of tile i2, 0: conv1 of tile i1
+        if (leader) {
+          if (i2 < i1 && mbar_test_wait(midfull, i2 & 1) && mbar_test_wait(a2free, (i2 & 1) ^ 1)) op = 1;
+          else if (i1 < my_tiles && mbar_test_wait(xfull, i1 & 1) && mbar_test_wait(a1free, (i1 & 1) ^ 1)) op = 0;
+          else continue;
+          ord[nd & 63u] = (uint8_t)op;
+          __threadfence_block();
+          *ord_n = nd + 1u;
+        } else {
+          while (*ord_n <= nd) {}
+          __threadfence_block();
+          op = ord[nd & 63u];
+          if (op) { mbar_wait(midfull, i2 & 1); mbar_wait(a2free, (i2 & 1) ^ 1); }
+          else { mbar_wait(xfull, i1 & 1); mbar_wait(a1free, (i1 & 1) ^ 1); }
+        }
+        ++nd;
+        tc_fence_after();
+        if (op) {                                              // M2(i2): conv2
           conv(1, tmem_u + ACC + ms0 * 2 * C, smem_u32(mid), Cfg::MPLANE, 1);
           umma_commit(midfree);
           umma_commit(a2full);
           ++i2;
-        } else if (i1 < my_tiles && mbar_test_wait(xfull, i1 & 1) && mbar_test_wait(a1free, (i1 & 1) ^ 1)) {   // M1(i1): conv1
-          tc_fence_after();
+        } else {                                               // M1(i1): conv1
           conv(0, tmem_u + ms0 * 2 * C, smem_u32(xwin), Cfg::XPLANE, p.dil);
           umma_commit(xempty);
           umma_commit(a1full);
