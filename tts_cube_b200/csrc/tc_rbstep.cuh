@@ -14,12 +14,14 @@
 // [2][B][L][C], exactly as tc_conv_kernel's TC_EPI_CONV leaves them; arithmetic is the same error-compensated
 // a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with fp32 accumulation in TMEM.
 //
-// Roles (608 threads): warp 0 = TMA producer (x window, one weight ring per conv), warps 1 and 18 = MMA issuers (half of the
-// sub-tiles each), warps 2-17 = epilogue.  Per tile: X (window load) -> M1 (conv1) -> E1 (a1 to shared memory) -> M2 (conv2)
-// -> E2 (x' to global).  Buffers are single (x window, a1, acc1, acc2), so tile i+1's M1 overlaps tile i's E1 / M2 / E2; the
-// ORDER of M1(i+1) and M2(i) (and of E1 / E2) is decided at run time by what is ready, every role polling with
-// mbarrier.test_wait: with a fixed order conv2 waited for the next tile's window load and the k = 3 steps ran at 18 % tensor
-// activity.
+// Roles (608 threads): warp 0 = TMA producer (x window, weight ring), warps 1 and 18 = MMA issuers (half of the sub-tiles
+// each), warps 2-17 = epilogue.  Software pipeline over the tiles of a CTA (it = tile counter):
+//     producer :  X(it)  W1(it)  W2(it-1)
+//     MMA      :  M1(it)         M2(it-1)          (conv1 of the next tile is issued BEFORE conv2 of this one, so the
+//     epilogue :  E1(it)         E2(it-1)           tensor pipe runs M1(it) while E1(it-1)'s a1 tiles are being written)
+// A run-time order (whichever of M1(it+1) / M2(it) is ready first; one weight ring per conv; issuer B following issuer A's
+// decision log, because two issuers taking different orders deadlock on the shared weight rings) was built and measured in
+// round 2: parity-green and 16 % MORE cycles (half-depth weight rings, polling), so the fixed order stays (git history).
 // What a narrow MMA costs (tools/umma_microbench.cu, profiles/r2_umma_microbench_*.txt): the tensor core needs 40 / 48 / 65 / 129
 // cycles for N = 32 / 64 / 128 / 256 (operand fetch at 128 B/clk, then math), but ONE issuing thread needs 51 cycles per MMA with
 // its descriptors ready and 75 when it builds them per MMA.  Hence: descriptors once per (tap, chunk) + one integer add per MMA
@@ -45,13 +47,12 @@ template <int C, int NSUB> struct RbCfg {
   static constexpr int MID = NCH * 2 * MPLANE + 1024;              // + slack: the last tap of the last sub-tile reads 2 h2 rows past the end
   static constexpr int WIMG = 2 * C * BK * 2;                      // (hi, lo) image of one (tap, chunk): C rows x 32 ch
   static constexpr int WS_ = (222 * 1024 - XWIN - MID - 1024) / WIMG;
-  static constexpr int WS = (WS_ > 12 ? 12 : WS_) / 2 * 2;         // weight slots: two rings of WS/2 (conv1 images, conv2 images)
-  static constexpr int WH = WS / 2;
+  static constexpr int WS = WS_ > 12 ? 12 : WS_;                   // weight ring depth
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM = 1024 + XWIN + MID + WS * WIMG + BAR_BYTES + 2 * C * 8;
   static constexpr int ACC = NSUB * 2 * C;                         // columns of one accumulator: per sub-tile [hi*hi + lo*hi | hi*lo]
   static_assert(2 * ACC == 512, "TMEM budget");
-  static_assert(WH >= 2, "weight rings too shallow");
+  static_assert(WS >= 4, "weight ring too shallow");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -81,7 +82,7 @@ constexpr int RB_ISSUERS = 2;
 template <int C, int NSUB>
 __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_constant__ RbParams p) {
   using Cfg = RbCfg<C, NSUB>;
-  constexpr int NCH = Cfg::NCH, NBOX = Cfg::NBOX, WS = Cfg::WS, WH = Cfg::WH, ACC = Cfg::ACC;
+  constexpr int NCH = Cfg::NCH, NBOX = Cfg::NBOX, WS = Cfg::WS, ACC = Cfg::ACC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* xwin = smem;                                   // [NCH][hi, lo][NBOX boxes]
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(wring + WS * Cfg::WIMG);
   uint64_t* xfull = bars;                // [1]
   uint64_t* xempty = bars + 1;           // [1]
-  uint64_t* wfull = bars + 2;            // [WS]: slots [0, WH) = conv1's ring, [WH, WS) = conv2's ring
+  uint64_t* wfull = bars + 2;            // [WS]
   uint64_t* wempty = wfull + WS;         // [WS]
   uint64_t* a1full = wempty + WS;        // [1]  MMA -> epilogue
   uint64_t* a1free = a1full + 1;         // [1]  epilogue (16 warps) -> MMA
@@ -99,12 +100,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
   uint64_t* midfull = a2free + 1;        // [1]  epilogue (16 warps) -> MMA
   uint64_t* midfree = midfull + 1;       // [1]  MMA -> epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(midfree + 1);
-  // the order of the MMA phases is decided by issuer A and FOLLOWED by issuer B (a log of 64 decisions in shared memory): both
-  // consume the same weight rings, whose slots are recycled only when BOTH have read them - two issuers taking different orders
-  // (one in conv1 waiting for ring-1 slots the other has not released, the other in conv2 waiting for ring-2 slots) deadlock
-  volatile uint32_t* ord_n = reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 384);
-  volatile uint8_t* ord = reinterpret_cast<volatile uint8_t*>(bars) + 392;
-  static_assert((2 + 2 * WS + 6) * 8 + 8 <= 384 && 392 + 64 <= Cfg::BAR_BYTES, "barrier block");
+  static_assert((2 + 2 * WS + 6) * 8 + 8 <= Cfg::BAR_BYTES, "barrier block");
   float2* sb1 = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);   // [C] (de-scale, bias) of conv1
   float2* sb2 = sb1 + C;
 
@@ -122,7 +118,6 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
     mbar_init(a1full, RB_ISSUERS); mbar_init(a1free, NUM_EPI_WARPS);
     mbar_init(a2full, RB_ISSUERS); mbar_init(a2free, NUM_EPI_WARPS);
     mbar_init(midfull, NUM_EPI_WARPS); mbar_init(midfree, RB_ISSUERS);
-    *ord_n = 0u;
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -138,39 +133,40 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      // three independent streams, each paced by its own consumer: the x window of the next tile (free once conv1 of the
-      // previous tile has read the buffer), conv1's weight images and conv2's weight images (one ring each: the issuers
-      // decide at run time whether conv1 of tile i+1 or conv2 of tile i goes first, so the two cannot share a FIFO).
-      // Every probe is a test_wait: a try_wait may suspend the thread on one barrier while another stream could move.
-      const int per_conv = p.k * NCH;                        // weight images of one conv of one tile
-      const long long tot = (long long)my_tiles * per_conv;
-      int x_next = 0;
-      long long w_i[2] = {0, 0};
-      while (x_next < my_tiles || w_i[0] < tot || w_i[1] < tot) {
-        if (x_next < my_tiles && mbar_test_wait(xempty, (x_next & 1) ^ 1)) {
-          const int tile = (int)blockIdx.x + x_next * (int)gridDim.x;
-          const int tt = tile % p.t_tiles, b = tile / p.t_tiles;
-          const int r0 = tt * R_OUT - h2 - h1;               // first row of the x window
-          mbar_expect_tx(xfull, Cfg::XWIN);
-          for (int cc = 0; cc < NCH; ++cc)
-            for (int bx = 0; bx < NBOX; ++bx) {
-              tma_load_3d(xwin + (cc * 2 + 0) * Cfg::XPLANE + bx * A_TILE_BYTES, &p.tmX, xfull, cc * BK, r0 + bx * BM, b);
-              tma_load_3d(xwin + (cc * 2 + 1) * Cfg::XPLANE + bx * A_TILE_BYTES, &p.tmX, xfull, cc * BK, r0 + bx * BM, p.B + b);
-            }
-          ++x_next;
-        }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          if (w_i[r] < tot) {
-            const int s = r * WH + (int)(w_i[r] % WH);
-            if (mbar_test_wait(&wempty[s], (uint32_t)((w_i[r] / WH) & 1) ^ 1)) {
-              const int img = (int)(w_i[r] % per_conv);
-              mbar_expect_tx(&wfull[s], Cfg::WIMG);
-              bulk_load(wring + s * Cfg::WIMG, (r == 0 ? p.W1 : p.W2) + (size_t)img * (Cfg::WIMG / 2), Cfg::WIMG, &wfull[s]);
-              ++w_i[r];
-            }
+      uint32_t iw = 0;
+      int x_next = 0;                                         // next tile whose x window has not been requested yet
+      // the x window of tile x_next may be loaded as soon as conv1 of tile x_next-1 has read the buffer; that moment falls
+      // in the middle of this thread's weight streaming (which is paced by the MMAs), so every wait polls for it
+      auto try_x = [&](bool block) {
+        if (x_next >= my_tiles) return;
+        const uint32_t par = (x_next & 1) ^ 1;
+        if (block) mbar_wait(xempty, par);
+        else if (!mbar_test_wait(xempty, par)) return;      // a probe, never a sleep: this thread is also feeding the weight ring
+        const int tile = (int)blockIdx.x + x_next * (int)gridDim.x;
+        const int tt = tile % p.t_tiles, b = tile / p.t_tiles;
+        const int r0 = tt * R_OUT - h2 - h1;                 // first row of the x window
+        mbar_expect_tx(xfull, Cfg::XWIN);
+        for (int cc = 0; cc < NCH; ++cc)
+          for (int bx = 0; bx < NBOX; ++bx) {
+            tma_load_3d(xwin + (cc * 2 + 0) * Cfg::XPLANE + bx * A_TILE_BYTES, &p.tmX, xfull, cc * BK, r0 + bx * BM, b);
+            tma_load_3d(xwin + (cc * 2 + 1) * Cfg::XPLANE + bx * A_TILE_BYTES, &p.tmX, xfull, cc * BK, r0 + bx * BM, p.B + b);
           }
+        ++x_next;
+      };
+      auto weights = [&](const __half* W) {                 // the k * NCH images of one conv, in the MMA thread's order
+        for (int img = 0; img < p.k * NCH; ++img, ++iw) {
+          const int s = iw % WS;
+          while (!mbar_test_wait(&wempty[s], ((iw / WS) & 1) ^ 1)) try_x(false);
+          mbar_expect_tx(&wfull[s], Cfg::WIMG);
+          bulk_load(wring + s * Cfg::WIMG, W + (size_t)img * (Cfg::WIMG / 2), Cfg::WIMG, &wfull[s]);
         }
+      };
+      for (int it = 0; it <= my_tiles; ++it) {
+        if (it < my_tiles) {
+          if (x_next <= it) try_x(true);                      // X(it), unless it went out early
+          weights(p.W1);
+        }
+        if (it > 0) weights(p.W2);
       }
     }
   } else if (warp == 1 || warp == NUM_THREADS / 32) {
@@ -184,14 +180,14 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
     if (lane == 0) {
       constexpr uint32_t idesc_cat = make_idesc(2 * C, BM);     // a_hi x [w_hi | w_lo]
       constexpr uint32_t idesc_one = make_idesc(C, BM);         // a_lo x w_hi
-      long long iw[2] = {0, 0};                            // images consumed from conv1's / conv2's ring
-      // one conv over this issuer's sub-tiles: A planes at a_base (+ cc*2*plane_bytes), tap j starts `tap_rows * j` rows in
-      auto conv = [&](int ring, uint32_t d_tmem, uint32_t a_base, uint32_t plane_bytes, int tap_rows) {
+      uint32_t iw = 0;
+      // one conv over the NSUB sub-tiles: A planes at a_base (+ cc*2*plane_bytes), tap j starts `tap_rows * j` rows in
+      auto conv = [&](uint32_t d_tmem, uint32_t a_base, uint32_t plane_bytes, int tap_rows) {
         uint32_t accumulate = 0;
         for (int tap = 0; tap < p.k; ++tap)
-          for (int cc = 0; cc < NCH; ++cc, ++iw[ring]) {
-            const int s = ring * WH + (int)(iw[ring] % WH);
-            mbar_wait(&wfull[s], (uint32_t)((iw[ring] / WH) & 1));
+          for (int cc = 0; cc < NCH; ++cc, ++iw) {
+            const int s = iw % WS;
+            mbar_wait(&wfull[s], (iw / WS) & 1);
             tc_fence_after();
             const uint32_t b_hi = smem_u32(wring + s * Cfg::WIMG);      // [w_hi: C rows][w_lo: C rows], one K-major tile of 2C rows
             const uint32_t a_hi0 = a_base + (uint32_t)(cc * 2) * plane_bytes + (uint32_t)(tap * tap_rows) * ROW_BYTES;
@@ -213,40 +209,23 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
             umma_commit(&wempty[s]);
           }
       };
-      // Dynamic order: conv2 of tile i2 as soon as its a1 tiles are in shared memory (and acc2 is drained), else conv1 of
-      // tile i1 as soon as its x window has landed (and acc1 is drained).  A fixed "M1(i+1) then M2(i)" order made conv2 wait
-      // for the NEXT tile's window load - the short k = 3 steps ran at 18 % tensor activity that way.
-      int i1 = 0, i2 = 0;
-      uint32_t nd = 0;                                         // decisions made (issuer A) / followed (issuer B)
-      const bool leader = warp == 1;
-      while (i2 < my_tiles) {
-        int op;                                                // 1: conv2 of tile i2, 0: conv1 of tile i1
-        if (leader) {
-          if (i2 < i1 && mbar_test_wait(midfull, i2 & 1) && mbar_test_wait(a2free, (i2 & 1) ^ 1)) op = 1;
-          else if (i1 < my_tiles && mbar_test_wait(xfull, i1 & 1) && mbar_test_wait(a1free, (i1 & 1) ^ 1)) op = 0;
-          else continue;
-          ord[nd & 63u] = (uint8_t)op;
-          __threadfence_block();
-          *ord_n = nd + 1u;
-        } else {
-          while (*ord_n <= nd) {}
-          __threadfence_block();
-          op = ord[nd & 63u];
-          if (op) { mbar_wait(midfull, i2 & 1); mbar_wait(a2free, (i2 & 1) ^ 1); }
-          else { mbar_wait(xfull, i1 & 1); mbar_wait(a1free, (i1 & 1) ^ 1); }
-        }
-        ++nd;
-        tc_fence_after();
-        if (op) {                                              // M2(i2): conv2
-          conv(1, tmem_u + ACC + ms0 * 2 * C, smem_u32(mid), Cfg::MPLANE, 1);
-          umma_commit(midfree);
-          umma_commit(a2full);
-          ++i2;
-        } else {                                               // M1(i1): conv1
-          conv(0, tmem_u + ms0 * 2 * C, smem_u32(xwin), Cfg::XPLANE, p.dil);
+      for (int it = 0; it <= my_tiles; ++it) {
+        if (it < my_tiles) {                                   // M1(it): conv1 of tile it
+          mbar_wait(a1free, (it & 1) ^ 1);                     // E1(it-1) has drained acc1
+          mbar_wait(xfull, it & 1);
+          tc_fence_after();
+          conv(tmem_u + ms0 * 2 * C, smem_u32(xwin), Cfg::XPLANE, p.dil);
           umma_commit(xempty);
           umma_commit(a1full);
-          ++i1;
+        }
+        if (it > 0) {                                          // M2(it-1): conv2 of the previous tile
+          const int jt = it - 1;
+          mbar_wait(a2free, (jt & 1) ^ 1);                     // E2(jt-1) has drained acc2
+          mbar_wait(midfull, jt & 1);
+          tc_fence_after();
+          conv(tmem_u + ACC + ms0 * 2 * C, smem_u32(mid), Cfg::MPLANE, 1);
+          umma_commit(midfree);
+          umma_commit(a2full);
         }
       }
     }
@@ -259,17 +238,9 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
     const int row = q * 32 + lane;          // row inside the sub-tile
     const int m = ms * BM + row;            // row inside the tile's NSUB*128 rows
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    // same dynamic order as the issuers (warp-uniform decision: tcgen05.ld is .sync.aligned): the epilogue of conv2 of tile e2
-    // when its accumulator is complete, else the epilogue of conv1 of tile e1
-    int e1 = 0, e2 = 0;
-    while (e2 < my_tiles) {
-      const bool run2 = e2 < e1 && __all_sync(0xffffffffu, mbar_test_wait(a2full, e2 & 1));
-      // E1 may run at most one tile ahead of E2: E1(e1) ends by waiting for conv2 of tile e1-1 to release the a1 buffer, and that
-      // conv2 cannot be issued before E2(e1-2) has drained acc2 - a warp that went further ahead would wait for itself
-      const bool run1 = !run2 && e1 < my_tiles && e1 <= e2 + 1 && __all_sync(0xffffffffu, mbar_test_wait(a1full, e1 & 1));
-      if (run1) {
+    for (int it = 0; it <= my_tiles; ++it) {
+      if (it < my_tiles) {
         // ---------------- E1(it): a1 = lrelu(conv1 + b1) -> shared-memory A tiles of conv2 ----------------
-        const int it = e1++;
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
         const int tt = tile % p.t_tiles, b = tile / p.t_tiles;
         const int t = tt * R_OUT - h2 + m;                     // time step of this a1 row
@@ -311,9 +282,9 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(midfull);
       }
-      if (run2) {
-        // ---------------- E2(jt): x' = conv2 + b2 + x -> global ----------------
-        const int jt = e2++;
+      if (it > 0) {
+        // ---------------- E2(it-1): x' = conv2 + b2 + x -> global ----------------
+        const int jt = it - 1;
         const int tile = (int)blockIdx.x + jt * (int)gridDim.x;
         const int tt = tile % p.t_tiles, b = tile / p.t_tiles;
         const int t = tt * R_OUT + m;
