@@ -727,6 +727,43 @@ def test_mel_copy_synthesis_chain(dev, neb):
     assert float((wav - ref).abs().max()) <= TOL
 
 
+_BITS_SCRIPT = """
+import hashlib, sys, torch
+sys.path[:0] = [%r, %r]
+from conftest import load_staged
+from oracle import hifigan_ref as H
+import tts_cube_b200 as cube
+sd = load_staged("g_00600000")
+cfg = dict(H.CONFIG_NEB)
+if sd is None:   # no trained checkpoint staged: seeded random weights, 64- and 32-channel stages included
+    cfg = dict(H.CONFIG_V1, upsample_initial_channel=128)
+    sd = H.random_state_dict(cfg, seed=21, std=0.3, g_scale=0.25)
+g = cube.CubeGenerator(cfg, math=1).to("cuda:0"); g.load_state_dict(sd); g.eval()
+mel = H.synthetic_mel(3, 70, seed=5)
+with torch.no_grad():
+    y = g(mel.to("cuda:0"), n_frames=[70, 9, 41]).cpu().contiguous()
+print("SHA", hashlib.sha256(y.numpy().tobytes()).hexdigest(), float(y.abs().max()))
+"""
+
+
+def test_packed_step_epilogue_is_bit_identical():
+    """tc_rbstep_kernel<.., PK> only regroups the epilogue's fp32 operations into packed instructions and turns selects into
+    branches around the stores: on the trained generator (ragged batch) the waveform must not change by one bit."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    script = _BITS_SCRIPT % (here, os.path.dirname(here))
+    out = {}
+    for pk in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", script], env=dict(os.environ, CUBE_RB_PK=pk), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (r.stdout + r.stderr)[-1500:]
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("SHA")][-1].split()
+        out[pk] = line[1]
+        assert float(line[2]) > 0.01
+    assert out["0"] == out["1"]
+
+
 # ------------------------------------------------ kernel variants behind env switches ------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("env,select", [
@@ -734,6 +771,9 @@ def test_mel_copy_synthesis_chain(dev, neb):
     pytest.param({"CUBE_TC_FUSED": "0", "CUBE_TC_CG2": "1"}, "student and tcgen05 and not full_length", id="student_cta_pair"),
     pytest.param({"CUBE_TC_WIN": "0"}, "hifigan and tcgen05 and not full_size and not loudness", id="hifigan_no_window"),
     pytest.param({"CUBE_TC_RBFUSE": "0"}, "hifigan and tcgen05 and not loudness", id="hifigan_unfused_resblock_steps"),
+    pytest.param({"CUBE_TC_WIDE": "1"}, "hifigan and tcgen05 and not loudness", id="hifigan_two_subtile_wide_stages"),
+    pytest.param({"CUBE_RB_PK": "1"}, "hifigan and tcgen05 and not loudness", id="hifigan_packed_step_epilogue"),
+    pytest.param({"CUBE_RB_PK": "1", "CUBE_TC_WIDE": "1"}, "hifigan and tcgen05 and not full_size", id="hifigan_packed_and_wide"),
     pytest.param({"CUBE_TC_FP8": "0"}, "student and tcgen05", id="student_pair_fp16x3"),
     pytest.param({"CUBE_TC_AONCE": "1"}, "student and tcgen05", id="student_pair_a_once"),
     pytest.param({"CUBE_TC_AONCE": "1", "CUBE_TC_FP8": "0"}, "student and tcgen05 and not 862", id="student_pair_a_once_fp16x3"),

@@ -289,6 +289,10 @@ static int dev_upload_bytes(cube_voc* h, const void* src, size_t bytes, void** o
   return 0;
 }
 
+static bool use_win(const cube_voc* h);
+static bool use_cg2();
+static bool use_wide();
+
 static int pack_tc_multi(cube_voc* h, const std::vector<std::vector<float>>& dense, const std::vector<float>& bias, int N,
                          int nchunks, int bn, TcPacked* out) {
   using namespace tc;
@@ -426,7 +430,7 @@ static int make_tmap_q8(CUtensorMap* tm, const uint8_t* base, int B, int T, int 
 }
 
 // Conv1d weight [M][C][K] -> tcgen05 images; K order = tap-major, channels padded to BK per tap
-static int pack_tc_conv1d(cube_voc* h, const std::string& base, int M, int C, int K, TcPacked* out) {
+static int pack_tc_conv1d(cube_voc* h, const std::string& base, int M, int C, int K, TcPacked* out, int bn_cap = 256) {
   using namespace tc;
   HostTensor w; const HostTensor* b;
   if (get_weight(h, base, &w) || expect_shape(base, w, {M, C, K}) || get_bias(h, base, M, &b)) return 1;
@@ -435,7 +439,7 @@ static int pack_tc_conv1d(cube_voc* h, const std::string& base, int M, int C, in
   for (int m = 0; m < M; ++m)
     for (int c = 0; c < C; ++c)
       for (int k = 0; k < K; ++k) D[0][(size_t)m * Kp + (size_t)k * Cp + c] = w.data[((size_t)m * C + c) * K + k];
-  if (pack_tc_multi(h, D, b->data, M, nch, std::min(256, M), out)) return 1;
+  if (pack_tc_multi(h, D, b->data, M, nch, std::min(bn_cap, M), out)) return 1;
   out->nseg = 1;
   out->seg[0] = {K, 1, 0, cpt, ((C - (cpt - 1) * BK) + 15) / 16};
   return 0;
@@ -615,6 +619,8 @@ static int finalize_hifigan(cube_voc* h) {
     h->tc_ups.resize(c.n_ups);
     h->tc_c1.assign(c.n_ups * nk, {});
     h->tc_c2.assign(c.n_ups * nk, {});
+    // ResBlock convs of stages wider than 128 channels as 128-column tiles when the wide variant will run them (launch_tc_bn)
+    const int rb_bn = (use_wide() && use_win(h) && !use_cg2()) ? 128 : 256;
     int cc = C0;
     for (int i = 0; i < c.n_ups; ++i) {
       if (pack_tc_convT(h, "ups." + std::to_string(i), cc, cc / 2, c.upsample_kernel_sizes[i], c.upsample_rates[i], &h->tc_ups[i])) return 1;
@@ -624,8 +630,8 @@ static int finalize_hifigan(cube_voc* h) {
         h->tc_c1[idx].resize(nd); h->tc_c2[idx].resize(nd);
         for (int m = 0; m < nd; ++m) {
           const std::string rb = "resblocks." + std::to_string(idx);
-          if (pack_tc_conv1d(h, rb + ".convs1." + std::to_string(m), cc, cc, k, &h->tc_c1[idx][m])) return 1;
-          if (pack_tc_conv1d(h, rb + ".convs2." + std::to_string(m), cc, cc, k, &h->tc_c2[idx][m])) return 1;
+          if (pack_tc_conv1d(h, rb + ".convs1." + std::to_string(m), cc, cc, k, &h->tc_c1[idx][m], rb_bn)) return 1;
+          if (pack_tc_conv1d(h, rb + ".convs2." + std::to_string(m), cc, cc, k, &h->tc_c2[idx][m], rb_bn)) return 1;
         }
       }
     }
@@ -1024,27 +1030,53 @@ static bool use_rbstep() {
   return v == 1;
 }
 
-template <int C, int NSUB>
-static int launch_rbstep(cube_voc* h, tc::RbParams& rp, cudaStream_t st) {
+// packed-fp32 epilogue of the fused step kernel (tc_rbstep.cuh, PK): CUBE_RB_PK=0/1 overrides the default
+#ifndef CUBE_RB_PK_DEFAULT
+#define CUBE_RB_PK_DEFAULT 0   // until a B200 session has run the parity suite with it
+#endif
+static bool use_rb_pk() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CUBE_RB_PK"); v = e ? (e[0] == '1' ? 1 : 0) : CUBE_RB_PK_DEFAULT; }
+  return v == 1;
+}
+
+template <int C, int NSUB, bool PK>
+static int launch_rbstep_v(cube_voc* h, tc::RbParams& rp, cudaStream_t st) {
   using Cfg = tc::RbCfg<C, NSUB>;
   static bool attr[64] = {false};
   if (!attr[h->device & 63]) {
-    CU_TRY(cudaFuncSetAttribute(tc::tc_rbstep_kernel<C, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    CU_TRY(cudaFuncSetAttribute(tc::tc_rbstep_kernel<C, NSUB, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr[h->device & 63] = true;
   }
   const int r_out = NSUB * tc::BM - (rp.k - 1);
   rp.t_tiles = (rp.L + r_out - 1) / r_out;
   const long long tiles = (long long)rp.t_tiles * rp.B;
   const int grid = (int)std::min<long long>(tiles, h->sm_count);
-  tc::tc_rbstep_kernel<C, NSUB><<<grid, tc::RB_THREADS, Cfg::SMEM, st>>>(rp);
+  tc::tc_rbstep_kernel<C, NSUB, PK><<<grid, tc::RB_THREADS, Cfg::SMEM, st>>>(rp);
   return 0;
+}
+template <int C, int NSUB>
+static int launch_rbstep(cube_voc* h, tc::RbParams& rp, cudaStream_t st) {
+  return use_rb_pk() ? launch_rbstep_v<C, NSUB, true>(h, rp, st) : launch_rbstep_v<C, NSUB, false>(h, rp, st);
+}
+
+// WIDE variant of the 128-column tile (tc_conv.cuh, Cfg<.., MS>): two 128-row sub-tiles share every staged weight image.
+// HiFi-GAN's 128-channel stage, and its 256-channel stage packed as two 128-column tiles; CUBE_TC_WIDE=0 restores one sub-tile
+// per tile (and 256-column tiles for the 256-channel ResBlock convs)
+#ifndef CUBE_WIDE_DEFAULT
+#define CUBE_WIDE_DEFAULT 0   // until a B200 session has run the parity suite with it
+#endif
+static bool use_wide() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CUBE_TC_WIDE"); v = e ? (e[0] == '1' ? 1 : 0) : CUBE_WIDE_DEFAULT; }
+  return v == 1;
 }
 
 // tp.T = rows per batch item; fills t_tiles for the chosen variant and launches
-template <int TN>
+template <int TN, int MS = 0>
 static void launch_tc_t(cube_voc* h, tc::TcParams& tp, cudaStream_t st) {
   const int nph = tp.nphase > 0 ? tp.nphase : 1;
-  if (use_cg2()) {
+  if (MS == 0 && use_cg2()) {
     static bool attr2[64] = {false};
     if (!attr2[h->device & 63]) {
       cudaFuncSetAttribute(tc::tc_conv_kernel<TN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<TN, true>::SMEM);
@@ -1066,7 +1098,7 @@ static void launch_tc_t(cube_voc* h, tc::TcParams& tp, cudaStream_t st) {
     cudaLaunchKernelEx(&cfg, tc::tc_conv_kernel<TN, true>, tp);
     return;
   }
-  constexpr int rows1 = tc::BM * tc::Cfg<TN, false>::MSUB;
+  constexpr int rows1 = tc::BM * tc::Cfg<TN, false, MS>::MSUB;
   tp.t_tiles = (tp.T + rows1 - 1) / rows1;
   const long long tiles = (long long)tp.n_tiles * tp.t_tiles * tp.B * nph;
   const int grid = (int)std::min<long long>(tiles, h->sm_count);
@@ -1098,23 +1130,24 @@ static void launch_tc_t(cube_voc* h, tc::TcParams& tp, cudaStream_t st) {
     if (ok) {
       static bool attrw[64] = {false};
       if (!attrw[h->device & 63]) {
-        cudaFuncSetAttribute(tc::tc_conv_kernel<TN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WinCfg<TN>::SMEM);
+        cudaFuncSetAttribute(tc::tc_conv_kernel<TN, false, true, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WinCfg<TN, MS>::SMEM);
         attrw[h->device & 63] = true;
       }
-      tc::tc_conv_kernel<TN, false, true><<<grid, tc::NUM_THREADS, tc::WinCfg<TN>::SMEM, st>>>(wp);
+      tc::tc_conv_kernel<TN, false, true, MS><<<grid, tc::NUM_THREADS, tc::WinCfg<TN, MS>::SMEM, st>>>(wp);
       return;
     }
   }
   static bool attr[64] = {false};
   if (!attr[h->device & 63]) {
-    cudaFuncSetAttribute(tc::tc_conv_kernel<TN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<TN, false>::SMEM);
+    cudaFuncSetAttribute(tc::tc_conv_kernel<TN, false, false, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<TN, false, MS>::SMEM);
     attr[h->device & 63] = true;
   }
-  tc::tc_conv_kernel<TN, false><<<grid, tc::NUM_THREADS, tc::Cfg<TN, false>::SMEM, st>>>(tp);
+  tc::tc_conv_kernel<TN, false, false, MS><<<grid, tc::NUM_THREADS, tc::Cfg<TN, false, MS>::SMEM, st>>>(tp);
 }
 
 static void launch_tc_bn(cube_voc* h, int bn, tc::TcParams& tp, cudaStream_t st) {
   if (bn == 256) launch_tc_t<256>(h, tp, st);
+  else if (bn == 128 && use_wide() && use_win(h) && !use_cg2()) launch_tc_t<128, 2>(h, tp, st);
   else if (bn == 128) launch_tc_t<128>(h, tp, st);
   else if (bn == 64) launch_tc_t<64>(h, tp, st);
   else launch_tc_t<32>(h, tp, st);

@@ -47,14 +47,18 @@ __host__ __device__ constexpr int swz_off(int r, int k) {
 }
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BN * 8 /*scale,bias*/;
 // per-N-tile-width variants (HiFi-GAN stages have 256/128/64/32 output channels)
-template <int TN, bool CG2 = false> struct Cfg {
+// MS > 0 overrides the number of 128-row sub-tiles per scheduled tile: <128, false, 2> is the WIDE variant of the 128- and
+// 256-channel HiFi-GAN stages (the latter as two 128-column tiles).  With one sub-tile those convs re-stream the whole weight
+// set (k * C * 2C * 2 B: 0.7 MB at C = 128, k = 11) from L2 for every 128 rows, 45-53 B/clk per SM at the tensor core's pace -
+// the L2 -> SM fabric, not the tensor core, bounded them; two sub-tiles share every staged weight image.
+template <int TN, bool CG2 = false, int MS = 0> struct Cfg {
   static_assert(TN == 256 || TN == 128 || TN == 64 || TN == 32, "tile N");
   // CG2: a CTA pair computes a 256-row x TN tile with tcgen05.mma.cta_group::2; each CTA stages its own
   // 128 rows of A and HALF of the weight tile (the pair's tensor cores exchange the halves)
   static constexpr int B_BYTES = (CG2 ? TN / 2 : TN) * BK * 2;
   // narrow tiles are overhead-bound at 128 rows (a 128x32 tile is only 16 KB of output): a scheduled tile
   // then covers MSUB 128-row sub-tiles that share the staged weight chunk, the barriers and the tile setup
-  static constexpr int MSUB = TN == 32 ? 4 : (TN == 64 ? 2 : 1);
+  static constexpr int MSUB = MS > 0 ? MS : (TN == 32 ? 4 : (TN == 64 ? 2 : 1));
   static constexpr int A_BYTES = MSUB * A_TILE_BYTES;           // per plane
   static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int NSTAGE = (190 * 1024 / STAGE) > 8 ? 8 : (190 * 1024 / STAGE);
@@ -62,7 +66,8 @@ template <int TN, bool CG2 = false> struct Cfg {
   // CAT (tiles narrower than 256 columns, single CTA): the hi*hi and hi*lo passes are ONE MMA of N = 2 TN on the weight
   // image [w_hi rows | w_lo rows] - one fetch of a_hi for two products (shared memory feeds the tensor core at ~64 B/clk,
   // which is what bounds these MMAs) - into separate column halves that the epilogue adds; lo*hi follows with N = TN
-  static constexpr bool CAT = TN < 256 && !CG2;
+  // ... as long as the double-buffered accumulators of all sub-tiles still fit the 512 TMEM columns
+  static constexpr bool CAT = TN < 256 && !CG2 && 2 * MSUB * 2 * TN <= 512;
   static constexpr int ACC_COLS = CAT ? 2 * TN : TN;           // accumulator columns per 128-row sub-tile
   static constexpr int TMEM_COLS = 2 * MSUB * ACC_COLS;        // 256 or 512: double-buffered accumulators
 };
@@ -71,12 +76,12 @@ template <int TN, bool CG2 = false> struct Cfg {
 // row-offset smem descriptor (the 64B/128B swizzles are functions of the absolute shared-memory address, so a
 // descriptor may start at any row).  L2->smem traffic for A drops by ~taps (11x for the k=11 HiFi-GAN convs).
 // Two rings: A windows (big, few) and per-(chunk, tap) weight images (small, many).
-template <int TN> struct WinCfg {
-  static constexpr int MSUB = Cfg<TN, false>::MSUB;
+template <int TN, int MS = 0> struct WinCfg {
+  static constexpr int MSUB = Cfg<TN, false, MS>::MSUB;
   static constexpr int NBOX = MSUB + 1;                         // boxes per plane in an A slot (span <= 128 rows)
   static constexpr int A_SLOT = 2 * NBOX * A_TILE_BYTES;        // hi boxes, then lo boxes
   static constexpr int B_SLOT = 2 * TN * BK * 2;                // hi image, lo image
-  static constexpr int SA = TN == 128 ? 3 : 2;
+  static constexpr int SA = (TN == 128 && MSUB == 1) ? 3 : 2;
   static constexpr int SB_ = (190 * 1024 - SA * A_SLOT) / B_SLOT;
   static constexpr int SB = SB_ > 8 ? 8 : SB_;
   static constexpr int SMEM = SA * A_SLOT + SB * B_SLOT + 1024 + 256 + TN * 8;
@@ -425,20 +430,21 @@ __device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int TN, bool CG2 = false, bool WIN = false>
+template <int TN, bool CG2 = false, bool WIN = false, int MS = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcParams p) {
   static_assert(!(CG2 && WIN), "window mode is single-CTA");
-  constexpr int SA = WinCfg<TN>::SA, SB = WinCfg<TN>::SB;       // window mode rings
-  constexpr int A_SLOT = WinCfg<TN>::A_SLOT, B_SLOT = WinCfg<TN>::B_SLOT;
-  constexpr int A_LO_OFF = WinCfg<TN>::NBOX * A_TILE_BYTES;     // lo plane inside an A slot
-  constexpr int STAGES = WIN ? (SA + SB + 1) / 2 : Cfg<TN, CG2>::NSTAGE;    // barrier-array stride only, in window mode
-  constexpr int STAGE_BYTES = WIN ? (SA * A_SLOT + SB * B_SLOT + STAGES - 1) / STAGES : Cfg<TN, CG2>::STAGE;
-  constexpr int B_TILE_BYTES = Cfg<TN, CG2>::B_BYTES;
+  static_assert(!(CG2 && MS > 0), "the sub-tile override is single-CTA");
+  constexpr int SA = WinCfg<TN, MS>::SA, SB = WinCfg<TN, MS>::SB;       // window mode rings
+  constexpr int A_SLOT = WinCfg<TN, MS>::A_SLOT, B_SLOT = WinCfg<TN, MS>::B_SLOT;
+  constexpr int A_LO_OFF = WinCfg<TN, MS>::NBOX * A_TILE_BYTES;     // lo plane inside an A slot
+  constexpr int STAGES = WIN ? (SA + SB + 1) / 2 : Cfg<TN, CG2, MS>::NSTAGE;    // barrier-array stride only, in window mode
+  constexpr int STAGE_BYTES = WIN ? (SA * A_SLOT + SB * B_SLOT + STAGES - 1) / STAGES : Cfg<TN, CG2, MS>::STAGE;
+  constexpr int B_TILE_BYTES = Cfg<TN, CG2, MS>::B_BYTES;
   constexpr int BN = TN;
-  constexpr bool CAT = Cfg<TN, CG2>::CAT;
-  constexpr int ACCW = Cfg<TN, CG2>::ACC_COLS;
-  constexpr int MSUB = Cfg<TN, CG2>::MSUB;
-  constexpr int A_BYTES = Cfg<TN, CG2>::A_BYTES;
+  constexpr bool CAT = Cfg<TN, CG2, MS>::CAT;
+  constexpr int ACCW = Cfg<TN, CG2, MS>::ACC_COLS;
+  constexpr int MSUB = Cfg<TN, CG2, MS>::MSUB;
+  constexpr int A_BYTES = Cfg<TN, CG2, MS>::A_BYTES;
   constexpr int CTA_ROWS = MSUB * BM;               // rows this CTA owns in a scheduled tile
   constexpr int TILE_ROWS = CG2 ? 2 * CTA_ROWS : CTA_ROWS;   // rows of one scheduled tile (p.t_tiles counts these)
   extern __shared__ uint8_t smem_raw[];
@@ -476,7 +482,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
     fence_barrier_init();
   }
   if (warp == 1) {
-    if constexpr (CG2) tmem_alloc2(tmem_slot, Cfg<TN, CG2>::TMEM_COLS); else tmem_alloc(tmem_slot, Cfg<TN, CG2>::TMEM_COLS);
+    if constexpr (CG2) tmem_alloc2(tmem_slot, Cfg<TN, CG2, MS>::TMEM_COLS); else tmem_alloc(tmem_slot, Cfg<TN, CG2, MS>::TMEM_COLS);
   }
   tc_fence_before();
   __syncthreads();
@@ -989,7 +995,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
   if constexpr (CG2) cluster_sync_all();     // no CTA of the pair exits while the other may still signal it
   if (warp == 1) {
     tc_fence_after();
-    if constexpr (CG2) tmem_dealloc2(tmem_base, Cfg<TN, CG2>::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg<TN, CG2>::TMEM_COLS);
+    if constexpr (CG2) tmem_dealloc2(tmem_base, Cfg<TN, CG2, MS>::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg<TN, CG2, MS>::TMEM_COLS);
   }
 }
 

@@ -79,7 +79,28 @@ struct RbParams {
 constexpr int RB_THREADS = NUM_THREADS + 32;
 constexpr int RB_ISSUERS = 2;
 
-template <int C, int NSUB>
+// packed fp32 helpers of the PK epilogue (sm_100 FADD2 / FMUL2 / FFMA2: two IEEE round-to-nearest operations per instruction, so
+// every value is bit-identical to the scalar epilogue's)
+__device__ __forceinline__ float2 rb_f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
+// leaky ReLU with 0 < slope < 1 as max(v, slope v); its inverse (factor > 1) as min(a, factor a)
+__device__ __forceinline__ float2 rb_lrelu2(float2 v, float2 slope2) {
+  const float2 t = __fmul2_rn(v, slope2);
+  return make_float2(fmaxf(v.x, t.x), fmaxf(v.y, t.y));
+}
+__device__ __forceinline__ float2 rb_unlrelu2(float2 a, float2 inv2) {
+  const float2 t = __fmul2_rn(a, inv2);
+  return make_float2(fminf(a.x, t.x), fminf(a.y, t.y));
+}
+__device__ __forceinline__ void rb_split2(float2 v, uint32_t& hi2, uint32_t& lo2) {
+  hi2 = pack_h2_sat(v.x, v.y);
+  const float2 d = __ffma2_rn(unpack_h2(hi2), make_float2(-1.f, -1.f), v);   // v - fp16(v), one rounding as in split16x2
+  lo2 = pack_h2_sat(d.x, d.y);
+}
+
+// PK: the epilogue's fp32 arithmetic on channel PAIRS (packed instructions), masks as branches around the stores instead of a
+// select per value.  The 16 epilogue warps execute ~1100 instructions per tile each, and at k = 3 that - not the tensor pipe -
+// sets the tile period (profiles/r2_ncu_hot_rbstep32.txt); the packed form needs about a quarter fewer.
+template <int C, int NSUB, bool PK = false>
 __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_constant__ RbParams p) {
   using Cfg = RbCfg<C, NSUB>;
   constexpr int NCH = Cfg::NCH, NBOX = Cfg::NBOX, WS = Cfg::WS, ACC = Cfg::ACC;
@@ -122,8 +143,14 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   for (int i = threadIdx.x; i < C; i += RB_THREADS) {
-    sb1[i] = make_float2(__ldg(p.inv1 + i), __ldg(p.bias1 + i));
-    sb2[i] = make_float2(__ldg(p.inv2 + i), __ldg(p.bias2 + i));
+    if constexpr (PK) {   // per channel pair {inv_j, inv_j+1, bias_j, bias_j+1}: one 16-byte read feeds a packed FFMA
+      const int pr = i >> 1, hf = i & 1;
+      reinterpret_cast<float*>(sb1)[pr * 4 + hf] = __ldg(p.inv1 + i); reinterpret_cast<float*>(sb1)[pr * 4 + 2 + hf] = __ldg(p.bias1 + i);
+      reinterpret_cast<float*>(sb2)[pr * 4 + hf] = __ldg(p.inv2 + i); reinterpret_cast<float*>(sb2)[pr * 4 + 2 + hf] = __ldg(p.bias2 + i);
+    } else {
+      sb1[i] = make_float2(__ldg(p.inv1 + i), __ldg(p.bias1 + i));
+      sb2[i] = make_float2(__ldg(p.inv2 + i), __ldg(p.bias2 + i));
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -256,6 +283,15 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
           tmem_ld16(taddr + ci * 16, r);                       // a_hi*w_hi + a_lo*w_hi
           tmem_ld16(taddr + C + ci * 16, rb);                  // a_hi*w_lo
           tmem_ld_wait();
+          if constexpr (PK) {
+            const float2 slope2 = make_float2(p.slope, p.slope);
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const float4 s = reinterpret_cast<const float4*>(sb1)[(cc * 32 + ci * 16 + j) >> 1];
+              const float2 v = __ffma2_rn(__fadd2_rn(rb_f2(r[j], r[j + 1]), rb_f2(rb[j], rb[j + 1])), make_float2(s.x, s.y), make_float2(s.z, s.w));
+              rb_split2(rb_lrelu2(v, slope2), hi2[ci * 8 + (j >> 1)], lo2[ci * 8 + (j >> 1)]);   // rows outside the utterance: masked at the store
+            }
+          } else {
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
             const float2 s0 = sb1[cc * 32 + ci * 16 + j], s1 = sb1[cc * 32 + ci * 16 + j + 1];
@@ -265,6 +301,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
             v1 = v1 < 0.f ? v1 * p.slope : v1;
             split16x2(valid ? v0 : 0.f, valid ? v1 : 0.f, hi2[ci * 8 + (j >> 1)], lo2[ci * 8 + (j >> 1)]);
           }
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -272,11 +309,20 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
         mbar_wait(midfree, (it & 1) ^ 1);                      // conv2 of the previous tile has read the a1 tiles
         // K-major SWIZZLE_64B tile [128 rows][32 ch]: 16-byte piece c16 of row r lives at piece c16 ^ ((r >> 1) & 3)
         uint8_t* mt = mid + (cc * 2) * Cfg::MPLANE + ms * A_TILE_BYTES;
+        if (PK && !valid) {                                    // a1 outside the utterance is conv2's zero padding
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16) {
+            const uint32_t off = row * 64 + ((c16 ^ ((row >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(mt + off) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(mt + Cfg::MPLANE + off) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        } else {
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16) {
           const uint32_t off = row * 64 + ((c16 ^ ((row >> 1) & 3)) << 4);
           *reinterpret_cast<uint4*>(mt + off) = make_uint4(hi2[4 * c16], hi2[4 * c16 + 1], hi2[4 * c16 + 2], hi2[4 * c16 + 3]);
           *reinterpret_cast<uint4*>(mt + Cfg::MPLANE + off) = make_uint4(lo2[4 * c16], lo2[4 * c16 + 1], lo2[4 * c16 + 2], lo2[4 * c16 + 3]);
+        }
         }
         fence_proxy_async();                                   // generic-proxy writes -> visible to the tensor core
         __syncwarp();
@@ -300,6 +346,63 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
         mbar_wait(a2full, jt & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ACC + ms * 2 * C + cc * 32 + lane_addr;
+        if (PK && !p.acc32) {
+          // packed form of the steps that only hand x' to the next step (two launches in three): no running sum, no select per value
+          const float2 inv2 = make_float2(p.inv_slope, p.inv_slope), slope2 = make_float2(p.slope, p.slope);
+#pragma unroll
+          for (int ci = 0; ci < 2; ++ci) {
+            const int c0 = ci * 16;
+            uint32_t r[16], rb[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld16(taddr + C + c0, rb);
+            uint32_t rh[8], rl[8];
+            if (o_in) {
+#pragma unroll
+              for (int v = 0; v < 2; ++v) {
+                const uint4 a = reinterpret_cast<const uint4*>(p.x16 + rowoff + c0)[v];
+                const uint4 c = reinterpret_cast<const uint4*>(p.x16 + plane + rowoff + c0)[v];
+                rh[4 * v] = a.x; rh[4 * v + 1] = a.y; rh[4 * v + 2] = a.z; rh[4 * v + 3] = a.w;
+                rl[4 * v] = c.x; rl[4 * v + 1] = c.y; rl[4 * v + 2] = c.z; rl[4 * v + 3] = c.w;
+              }
+            } else {
+#pragma unroll
+              for (int v = 0; v < 8; ++v) rh[v] = rl[v] = 0u;
+            }
+            tmem_ld_wait();
+            if (ci == 1) {                                     // last TMEM read of this warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(a2free);
+            }
+            if (p.out16 && o_in) {
+              uint4* oh = reinterpret_cast<uint4*>(p.out16 + rowoff + c0);
+              uint4* ol = reinterpret_cast<uint4*>(p.out16 + plane + rowoff + c0);
+              if (o_valid) {
+                uint32_t h2_[8], l2_[8];
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  const float4 s = reinterpret_cast<const float4*>(sb2)[(cc * 32 + c0 + j) >> 1];
+                  const float2 a = rb_unlrelu2(__fadd2_rn(unpack_h2(rh[j >> 1]), unpack_h2(rl[j >> 1])), inv2);   // stored lrelu(x): invert
+                  const float2 w = __fadd2_rn(__ffma2_rn(__fadd2_rn(rb_f2(r[j], r[j + 1]), rb_f2(rb[j], rb[j + 1])), make_float2(s.x, s.y), make_float2(s.z, s.w)), a);
+                  rb_split2(rb_lrelu2(w, slope2), h2_[j >> 1], l2_[j >> 1]);
+                }
+#pragma unroll
+                for (int q4 = 0; q4 < 2; ++q4) {
+                  oh[q4] = make_uint4(h2_[4 * q4], h2_[4 * q4 + 1], h2_[4 * q4 + 2], h2_[4 * q4 + 3]);
+                  ol[q4] = make_uint4(l2_[4 * q4], l2_[4 * q4 + 1], l2_[4 * q4 + 2], l2_[4 * q4 + 3]);
+                }
+              } else {                                         // rows past the utterance's end are written as zero
+                oh[0] = make_uint4(0u, 0u, 0u, 0u); oh[1] = make_uint4(0u, 0u, 0u, 0u);
+                ol[0] = make_uint4(0u, 0u, 0u, 0u); ol[1] = make_uint4(0u, 0u, 0u, 0u);
+              }
+            }
+          }
+        } else {
+        // (de-scale, bias) of channel c in either layout of sb2
+        auto sb2s = [&](int c) -> float2 {
+          if constexpr (PK) { const float* f = reinterpret_cast<const float*>(sb2) + (c >> 1) * 4 + (c & 1); return make_float2(f[0], f[2]); }
+          else return sb2[c];
+        };
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
           const int c0 = ci * 16;
@@ -336,7 +439,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
-            const float2 s0 = sb2[cc * 32 + c0 + j], s1 = sb2[cc * 32 + c0 + j + 1];
+            const float2 s0 = sb2s(cc * 32 + c0 + j), s1 = sb2s(cc * 32 + c0 + j + 1);
             const float2 ah = unpack_h2(rh[j >> 1]), al = unpack_h2(rl[j >> 1]);
             float a0 = ah.x + al.x, a1 = ah.y + al.y;          // stored lrelu(x): invert
             a0 = a0 < 0.f ? a0 * p.inv_slope : a0;
@@ -384,6 +487,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) tc_rbstep_kernel(const __grid_c
             }
           }
         }
+        }   // generic (scalar) form
       }
     }
   }
