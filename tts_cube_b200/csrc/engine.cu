@@ -619,8 +619,10 @@ static int finalize_hifigan(cube_voc* h) {
     h->tc_ups.resize(c.n_ups);
     h->tc_c1.assign(c.n_ups * nk, {});
     h->tc_c2.assign(c.n_ups * nk, {});
-    // ResBlock convs of stages wider than 128 channels as 128-column tiles when the wide variant will run them (launch_tc_bn)
-    const int rb_bn = (use_wide() && use_win(h) && !use_cg2()) ? 128 : 256;
+    // The 256-channel stage keeps its 256-column tiles: as two 128-column tiles with two sub-tiles each it measured 25-30 %
+    // SLOWER (profiles/r2n_*: 226 / 451 / 663 us against 184 / 347 / 506 for k = 3 / 7 / 11) - its MMAs are already 81 % of the
+    // tensor pipe's time; the two-sub-tile variant is for the stage whose natural tile is 128 columns (launch_tc_bn)
+    const int rb_bn = 256;
     int cc = C0;
     for (int i = 0; i < c.n_ups; ++i) {
       if (pack_tc_convT(h, "ups." + std::to_string(i), cc, cc / 2, c.upsample_kernel_sizes[i], c.upsample_rates[i], &h->tc_ups[i])) return 1;
@@ -1016,6 +1018,16 @@ static bool use_fused() {
   return v < 0 ? CUBE_FUSED_DEFAULT : v == 1;
 }
 
+// lean issue loops of the tcgen05 kernels (tc_block.cuh, tc_conv.cuh window mode): CUBE_TC_LEAN=0/1 overrides the default
+#ifndef CUBE_LEAN_DEFAULT
+#define CUBE_LEAN_DEFAULT 0   // until a B200 session has run the parity suite with it
+#endif
+static bool use_lean() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CUBE_TC_LEAN"); v = e ? (e[0] == '1' ? 1 : 0) : CUBE_LEAN_DEFAULT; }
+  return v == 1;
+}
+
 static bool use_cg2() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("CUBE_TC_CG2"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -1061,8 +1073,7 @@ static int launch_rbstep(cube_voc* h, tc::RbParams& rp, cudaStream_t st) {
 }
 
 // WIDE variant of the 128-column tile (tc_conv.cuh, Cfg<.., MS>): two 128-row sub-tiles share every staged weight image.
-// HiFi-GAN's 128-channel stage, and its 256-channel stage packed as two 128-column tiles; CUBE_TC_WIDE=0 restores one sub-tile
-// per tile (and 256-column tiles for the 256-channel ResBlock convs)
+// For HiFi-GAN's 128-channel stage (-10 % per conv, profiles/r2n_*); CUBE_TC_WIDE=0/1 overrides the default
 #ifndef CUBE_WIDE_DEFAULT
 #define CUBE_WIDE_DEFAULT 0   // until a B200 session has run the parity suite with it
 #endif
@@ -1107,6 +1118,7 @@ static void launch_tc_t(cube_voc* h, tc::TcParams& tp, cudaStream_t st) {
     // wider dilations (ClariNet d = 81, 243) become single-tap segments
     tc::TcParams wp = tp;
     wp.nseg = 0;
+    wp.lean = use_lean() ? 1 : 0;
     int base = 0;
     bool ok = true;
     for (int s_ = 0; s_ < tp.nseg && ok; ++s_) {
@@ -1495,6 +1507,7 @@ static int forward_student(cube_voc* h, const float* mel, const int32_t* n_frame
         static int pfn = -1;        // L2 prefetch of the next tile's A rows by the epilogue warps; CUBE_TC_PREFETCH=0/1
         if (pfn < 0) { const char* e = getenv("CUBE_TC_PREFETCH"); pfn = (e && e[0] == '1') ? 1 : 0; }
         bp.prefetch_next = pfn; bp.c_in16 = c16; bp.c_ch = CI;
+        bp.lean = use_lean() ? 1 : 0;
         static int pairv = -1;      // CTA-pair (cta_group::2) tiling of the block kernel; CUBE_TC_PAIR=0: one CTA per tile
         if (pairv < 0) { const char* e = getenv("CUBE_TC_PAIR"); pairv = (e && e[0] == '0') ? 0 : 1; }
         const bool stats = block_stats_on();                             // instrumented build: wait cycles of CTA 0

@@ -78,6 +78,7 @@ struct BlockParams {
   const uint8_t* c8_in;
   int c_ch;                      // channels of the conditioning planes (80)
   unsigned long long* stats;     // STATS build only: wait-cycle counters of CTA 0 (CUBE_BLOCK_STATS=1), 24 slots
+  int lean;                      // 1: the MMA thread runs the short instruction stream (see "lean issue" in the kernel)
 };
 
 // wait on an mbarrier, charging the cycles to a counter slot in the instrumented build
@@ -257,7 +258,117 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_block_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0 && crank != 0) {             // (crank != 0 only exists with PAIR)
+    if (crank == 0 && p.lean) {
+      // Lean issue.  ONE thread issues every MMA of the CTA (pair), and its instruction stream - not the tensor core - set the
+      // pace: ncu shows the issuing warp busy all the time (hardly any barrier wait) at ~6 cycles per dependent instruction, and
+      // the generic loop below spends ~23 instructions per MMA (two descriptors built from addresses: shift, mask, or, 64-bit
+      // pack; the per-thread-to-uniform-register hand-over ELECT / 5 x R2UR.BROADCAST / branch in front of every MMA; a run-time
+      // K-step loop; modulo ring indices) = ~175 cycles per MMA against the 128.5 the tensor core needs.
+      // Here the WHOLE warp runs the loop: waits and counters are warp-uniform, so offsets and descriptors are computed on the
+      // uniform datapath and the MMAs of a stage issue back to back from uniform registers; one elected lane issues them and
+      // the commits.  ONE descriptor per swizzle mode for the start of shared memory, every operand = that + a byte offset
+      // (desc_add), K steps unrolled, ring stage / phase as counters.  Same MMAs, same order, same barriers as the generic loop.
+      constexpr uint32_t idesc = make_idesc(BN, TILE_ROWS);
+      constexpr uint32_t idesc8_0 = make_idesc_f8(BN, TILE_ROWS, 0), idesc8_1 = make_idesc_f8(BN, TILE_ROWS, 1);
+      (void)idesc8_0; (void)idesc8_1;
+      const uint64_t D16 = make_desc(smem_u32(smem)), D32 = make_desc32(smem_u32(smem));
+      (void)D32;
+      constexpr uint32_t O_OFF = NST * STG;                     // o_smem - smem
+      constexpr uint32_t A8 = A_TILE_BYTES, AH = A_TILE_BYTES / 2, BH = B_BYTES / 2;
+      (void)AH; (void)BH;
+      const bool leader = elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      uint32_t st = 0, ph = 0, titer = 0;                       // ring stage, parity of its current phase
+      uint32_t free_ph[2] = {0, 0};
+      uint32_t ofull_ph = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++titer) {
+        const int r0 = titer & 1, r1 = r0 ^ 1;
+        for (int pass = 0; pass < NPASS; ++pass) {
+#pragma unroll
+          for (int k = 0; k < NTP; ++k) {
+            const int rg = (AONCE ? k : pass) == 0 ? r0 : r1;
+            BLK_WAIT(&acc_free[rg], (free_ph[rg] & 1) ^ 1, AONCE ? k : pass);
+            ++free_ph[rg];
+          }
+          tc_fence_after();
+          uint32_t accumulate = 0;
+          for (int ch = 0; ch < nch1; ++ch) {                   // the producer's order: taps of h, then the conditioning
+            BLK_WAIT(&full[st], ph, 2);
+            if constexpr (PAIR) BLK_WAIT(&pfull[st], ph, 2);
+            tc_fence_after();
+            const uint32_t so = st * STG;
+            const int ksteps = ch != nch1 - 1 ? BK / 16 : p.c_last_ksteps;
+            if (leader) {
+#pragma unroll
+              for (int k = 0; k < NTP; ++k) {
+                const int rg = (AONCE ? k : pass) == 0 ? r0 : r1;
+                const uint32_t d_tmem = tmem_u + rg * BN;
+                const uint32_t bo = so + 2 * A_TILE_BYTES + k * 2 * B_BYTES;
+                if constexpr (Q8) {
+                  blk_mma_f16<PAIR>(d_tmem, desc_add(D16, so), desc_add(D16, bo), idesc, accumulate);
+                  if (ksteps > 1) blk_mma_f16<PAIR>(d_tmem, desc_add(D16, so + 32), desc_add(D16, bo + 32), idesc, 1);
+                  blk_mma_f8<PAIR>(d_tmem, desc_add(D32, so + A8), desc_add(D32, bo + B_BYTES), idesc8_0, 1);
+                  blk_mma_f8<PAIR>(d_tmem, desc_add(D32, so + A8 + AH), desc_add(D32, bo + B_BYTES + BH), idesc8_1, 1);
+                } else {
+#pragma unroll
+                  for (int ks = 0; ks < BK / 16; ++ks) {
+                    if (ks < ksteps) {
+                      const uint32_t ko = ks * 32;
+                      blk_mma_f16<PAIR>(d_tmem, desc_add(D16, so + ko), desc_add(D16, bo + ko), idesc, ks ? 1u : accumulate);
+                      blk_mma_f16<PAIR>(d_tmem, desc_add(D16, so + ko), desc_add(D16, bo + B_BYTES + ko), idesc, 1);
+                      blk_mma_f16<PAIR>(d_tmem, desc_add(D16, so + A8 + ko), desc_add(D16, bo + ko), idesc, 1);
+                    }
+                  }
+                }
+              }
+              blk_commit<PAIR>(&empty[st]);
+            }
+            accumulate = 1;
+            if (++st == NST) { st = 0; ph ^= 1; }
+          }
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < NTP; ++k) blk_commit<PAIR>(&acc_full[(AONCE ? k : pass) == 0 ? r0 : r1]);
+          }
+        }
+        {  // GEMM2 into r0 (drained by the gate epilogue of n-tile 0): K half kh uses the o half the epilogue staged
+          BLK_WAIT(&acc_free[r0], (free_ph[r0] & 1) ^ 1, 3);
+          ++free_ph[r0];
+          const uint32_t d_tmem = tmem_u + r0 * BN;
+          uint32_t accumulate = 0;
+          for (int kh = 0; kh < 2; ++kh) {
+            BLK_WAIT(o_full, ofull_ph & 1, 4 + kh);
+            ++ofull_ph;
+            tc_fence_after();
+#pragma unroll 1
+            for (int c4 = 0; c4 < 4; ++c4) {
+              BLK_WAIT(&full[st], ph, 6);
+              if constexpr (PAIR) BLK_WAIT(&pfull[st], ph, 6);
+              tc_fence_after();
+              const uint32_t ao = O_OFF + c4 * 2 * A_TILE_BYTES, bo = st * STG + 2 * A_TILE_BYTES;
+              if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < BK / 16; ++ks) {
+                  const uint32_t ko = ks * 32;
+                  blk_mma_f16<PAIR>(d_tmem, desc_add(D16, ao + ko), desc_add(D16, bo + ko), idesc, ks ? 1u : accumulate);
+                  blk_mma_f16<PAIR>(d_tmem, desc_add(D16, ao + ko), desc_add(D16, bo + B_BYTES + ko), idesc, 1);
+                  blk_mma_f16<PAIR>(d_tmem, desc_add(D16, ao + A8 + ko), desc_add(D16, bo + ko), idesc, 1);
+                }
+                blk_commit<PAIR>(&empty[st]);
+              }
+              accumulate = 1;
+              if (++st == NST) { st = 0; ph ^= 1; }
+            }
+            if (leader) blk_commit<PAIR>(o_free);          // the o half may be overwritten
+          }
+          if (leader) blk_commit<PAIR>(&acc_full[r0]);     // r|s accumulator complete
+        }
+      }
+      if (STATS && p.stats && blockIdx.x == 0 && leader) {
+        for (int i = 0; i < 7; ++i) atomicAdd(p.stats + 3 + i, (unsigned long long)st_acc[i]);
+        atomicAdd(p.stats + 10, (unsigned long long)(clock64() - st_begin));
+      }
+    } else if (lane == 0 && crank != 0) {             // (crank != 0 only exists with PAIR)
       // peer CTA: it issues no MMA; this thread relays "my stage has landed" to the leader
       uint32_t it = 0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step)

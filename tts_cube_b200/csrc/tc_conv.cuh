@@ -142,6 +142,7 @@ struct TcParams {
                             // the subnormal range for small activations); residual planes are read back with 1/S
   float* acc32; int acc_mode; float acc_div; int acc_store;
   __half* out16b;
+  int lean;                 // window mode: 1 = the MMA thread's short instruction stream ("lean issue" in the kernel)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -257,6 +258,19 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
 // completion of all MMAs issued so far by this thread -> one arrival on the mbarrier
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// one lane of a converged warp (elect.sync): the lane that issues the warp's MMAs and commits in the lean issue loops
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- 2-CTA (cta_group::2) variants ----
@@ -564,7 +578,71 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_conv_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    if (WIN && p.lean) {
+      // Lean issue (see tc_block.cuh): the issuing thread's instruction stream, not the tensor core, paced the window-mode convs -
+      // ncu on the 128-channel HiFi-GAN stage: tensor pipe 49 % active, the issuing warp never waiting, ~32 instructions per MMA
+      // (ring indices modulo 5, a run-time K-step loop, descriptors per tap, the per-thread-to-uniform hand-over in front of every
+      // MMA).  Here the WHOLE warp runs the loop (waits and counters are warp-uniform -> offsets and descriptors on the uniform
+      // datapath, the MMAs of a (chunk, tap) issue back to back) and one elected lane issues the MMAs and commits; one descriptor
+      // for the start of shared memory + byte offsets, K steps unrolled, ring slots / phases as counters.  Same MMAs, same order,
+      // same barriers as the generic loop below.
+      constexpr uint32_t idesc = make_idesc(TN, BM);
+      constexpr uint32_t idesc_cat = make_idesc(CAT ? 2 * TN : TN, BM);
+      (void)idesc_cat;
+      const uint64_t D16 = make_desc(smem_u32(smem));
+      const bool leader = elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      uint32_t sa = 0, pha = 0, sbi = 0, phb = 0, titer = 0;
+      // the MMAs of K step ks of one (chunk, tap): every sub-tile against the staged weight image
+      auto kstep = [&](uint32_t d_tmem, uint32_t ao, uint32_t bo, int ks, uint32_t acc) {
+        const uint32_t ko = ks * 32;
+#pragma unroll
+        for (int ms = 0; ms < MSUB; ++ms) {
+          const uint32_t a = ao + ms * A_TILE_BYTES + ko;
+          const uint32_t d = d_tmem + ms * ACCW;
+          if constexpr (CAT) {     // [w_hi | w_lo] is one K-major tile of 2 TN rows (the lo image follows the hi image)
+            umma_f16(d, desc_add(D16, a), desc_add(D16, bo + ko), idesc_cat, acc);
+            umma_f16(d, desc_add(D16, a + A_LO_OFF), desc_add(D16, bo + ko), idesc, 1);
+          } else {
+            umma_f16(d, desc_add(D16, a), desc_add(D16, bo + ko), idesc, acc);
+            umma_f16(d, desc_add(D16, a), desc_add(D16, bo + B_SLOT / 2 + ko), idesc, 1);
+            umma_f16(d, desc_add(D16, a + A_LO_OFF), desc_add(D16, bo + ko), idesc, 1);
+          }
+        }
+      };
+      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++titer) {
+        const uint32_t acc = titer & 1, aph = (titer >> 1) & 1;
+        mbar_wait(&tempty[acc], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_u + acc * (MSUB * ACCW);
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int taps = p.seg[s].taps, nchunks = p.seg[s].nchunks, last_ksteps = p.seg[s].last_ksteps;
+          const uint32_t tap_bytes = (uint32_t)p.seg[s].dil * ROW_BYTES;
+          for (int cc = 0; cc < nchunks; ++cc) {
+            mbar_wait(&fullA[sa], pha);
+            const int ksteps = cc != nchunks - 1 ? BK / 16 : last_ksteps;
+            uint32_t ao = sa * A_SLOT;                          // tap 0; every tap starts `dil` rows further into the window
+            for (int tap = 0; tap < taps; ++tap, ao += tap_bytes) {
+              mbar_wait(&fullB[sbi], phb);
+              tc_fence_after();
+              const uint32_t bo = SA * A_SLOT + sbi * B_SLOT;
+              if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < BK / 16; ++ks)
+                  if (ks < ksteps) kstep(d_tmem, ao, bo, ks, ks ? 1u : accumulate);
+                umma_commit(&emptyB[sbi]);
+              }
+              accumulate = 1;
+              if (++sbi == SB) { sbi = 0; phb ^= 1; }
+            }
+            if (leader) umma_commit(&emptyA[sa]);
+            if (++sa == SA) { sa = 0; pha ^= 1; }
+          }
+        }
+        if (leader) umma_commit(&tfull[acc]);
+      }
+    } else if (lane == 0) {
       if (CG2 && crank != 0) {
         // peer CTA of a pair: it issues no MMA; this thread relays "my stage is full" to the leader
         uint32_t it = 0;
