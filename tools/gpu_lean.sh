@@ -13,10 +13,13 @@ except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY
 }
+( time CUBE_TC_LEAN=1 timeout 90 python -c "import __graft_entry__ as g; g.smoke()" ) > $O/${TAG}_smoke_lean.log 2>&1
+rc=$?; tail -4 $O/${TAG}_smoke_lean.log | cut -c1-300
+if [ $rc -ne 0 ]; then echo "smoke with CUBE_TC_LEAN=1 failed (rc=$rc): stopping"; exit 1; fi
 for l in 0 1; do
-  CUBE_TC_LEAN=$l timeout 150 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_pwn_lean$l.json 2> $O/${TAG}_bench_pwn_lean$l.err
+  CUBE_TC_LEAN=$l timeout 90 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_pwn_lean$l.json 2> $O/${TAG}_bench_pwn_lean$l.err
   show $O/${TAG}_bench_pwn_lean$l.json "student lean=$l"
-  CUBE_TC_LEAN=$l timeout 100 python bench.py --workload hifigan --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > $O/${TAG}_bench_hifigan_lean$l.json 2> $O/${TAG}_bench_hifigan_lean$l.err
+  CUBE_TC_LEAN=$l timeout 60 python bench.py --workload hifigan --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > $O/${TAG}_bench_hifigan_lean$l.json 2> $O/${TAG}_bench_hifigan_lean$l.err
   show $O/${TAG}_bench_hifigan_lean$l.json "hifigan lean=$l"
 done
 CUBE_TC_LEAN=1 CUBE_TC_WIDE=1 timeout 100 python bench.py --workload hifigan --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > $O/${TAG}_bench_hifigan_lean1_wide1.json 2> $O/${TAG}_bench_hifigan_lean1_wide1.err
