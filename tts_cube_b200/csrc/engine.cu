@@ -1020,7 +1020,7 @@ static bool use_fused() {
 
 // lean issue loops of the tcgen05 kernels (tc_block.cuh, tc_conv.cuh window mode): CUBE_TC_LEAN=0/1 overrides the default
 #ifndef CUBE_LEAN_DEFAULT
-#define CUBE_LEAN_DEFAULT 0   // until a B200 session has run the parity suite with it
+#define CUBE_LEAN_DEFAULT 1   // B200 suite green with it (profiles/r2p_pytest_lean.log); student -6 % cycles per block launch, HiFi-GAN wide stages -8 %
 #endif
 static bool use_lean() {
   static int v = -1;
@@ -1044,7 +1044,7 @@ static bool use_rbstep() {
 
 // packed-fp32 epilogue of the fused step kernel (tc_rbstep.cuh, PK): CUBE_RB_PK=0/1 overrides the default
 #ifndef CUBE_RB_PK_DEFAULT
-#define CUBE_RB_PK_DEFAULT 0   // until a B200 session has run the parity suite with it
+#define CUBE_RB_PK_DEFAULT 0   // parity green and bit-identical on a B200 (profiles/r2n_*), but no measurable gain (31.5 vs 32.1 ms): opt-in
 #endif
 static bool use_rb_pk() {
   static int v = -1;
@@ -1075,7 +1075,7 @@ static int launch_rbstep(cube_voc* h, tc::RbParams& rp, cudaStream_t st) {
 // WIDE variant of the 128-column tile (tc_conv.cuh, Cfg<.., MS>): two 128-row sub-tiles share every staged weight image.
 // For HiFi-GAN's 128-channel stage (-10 % per conv, profiles/r2n_*); CUBE_TC_WIDE=0/1 overrides the default
 #ifndef CUBE_WIDE_DEFAULT
-#define CUBE_WIDE_DEFAULT 0   // until a B200 session has run the parity suite with it
+#define CUBE_WIDE_DEFAULT 1   // B200 parity green (profiles/r2n_pytest_variants.log, r2p_pytest_lean.log); 128-channel stage -10 % per conv
 #endif
 static bool use_wide() {
   static int v = -1;
