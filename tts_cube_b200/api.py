@@ -223,26 +223,39 @@ def synthesize(vocoder, mels: Optional[Sequence[torch.Tensor]], zs: Optional[Seq
 
 
 def cubegan_inference_batch(model, Xs: Sequence[dict], max_batch: int = 64, max_frames: Optional[int] = None,
-                            int16: bool = False, group=None) -> Optional[List[torch.Tensor]]:
+                            int16: bool = False, group=None, frontend_batch: int = 32) -> Optional[List[torch.Tensor]]:
     """BASELINE configs[4] glue: many utterances through the reference ``Cubegan`` whose ``_generator`` is a CubeGenerator
     (``install_into_cubegan``).  The reference frontend is batch-1 by construction (``Languasito2.inference`` squeezes the
-    duration matrix, cube/networks/modules.py:945-953), so it runs per utterance exactly as
-    ``Cubegan.inference`` runs it (cube/networks/cubegan.py:74-81: optional HF conditioning, ``_languasito.inference``,
-    the empty-utterance guard); the vocoder then takes ALL conditionings in length-sorted batches (each utterance computed
-    as if alone) - sharded over the ranks when torch.distributed is up (rank 0 holds ``Xs``).
+    duration matrix, cube/networks/modules.py:945-953).  When ``model._languasito`` has the reference layout without external
+    conditioning, its own modules are driven over padded batches of ``frontend_batch`` utterances, each computed as if alone
+    (tts_cube_b200/frontend.py; ``frontend_batch=0`` disables this); otherwise it runs per utterance exactly as
+    ``Cubegan.inference`` runs it (cube/networks/cubegan.py:74-81: optional HF conditioning, ``_languasito.inference``, the
+    empty-utterance guard).  The vocoder then takes ALL conditionings in length-sorted batches (each utterance computed as if
+    alone) - sharded over the ranks when torch.distributed is up (rank 0 holds ``Xs``).
     Returns the waveforms [T_i] (float32, or int16 with the ``*32767`` epilogue of cube/api.py:64-65) on rank 0."""
+    from . import frontend as FE
     from .heads import wav_to_int16
     conds = None
     if Xs is not None:
         conds = []
+        lang = model._languasito
+        hf = getattr(model, "_hf", None)
         with torch.no_grad():
-            for X in Xs:
-                hf = getattr(model, "_hf", None)
-                hf_cond = hf(X["x_tok_ids"])["last_hidden_state"] if hf is not None else None
-                c = model._languasito.inference(X, hf_cond=hf_cond)           # [1, F, 80]
-                if c.shape[1] == 0:
-                    c = torch.zeros((c.shape[0], 1, c.shape[2]), device=c.device)
-                conds.append(c[0].t())                                       # [80, F] view; padded / copied per batch
+            if frontend_batch > 0 and hf is None and FE.supports(lang):
+                for i0 in range(0, len(Xs), frontend_batch):
+                    part = Xs[i0:i0 + frontend_batch]
+                    cs = FE.languasito_inference_batch(lang, [X["x_char"][0] for X in part], [X["x_speaker"][0] for X in part])
+                    for c in cs:                                              # [F, 80]
+                        if c.shape[0] == 0:                                   # the empty-utterance guard of cubegan.py:78-80
+                            c = torch.zeros((1, c.shape[1]), device=c.device)
+                        conds.append(c.t())
+            else:
+                for X in Xs:
+                    hf_cond = hf(X["x_tok_ids"])["last_hidden_state"] if hf is not None else None
+                    c = lang.inference(X, hf_cond=hf_cond)                    # [1, F, 80]
+                    if c.shape[1] == 0:
+                        c = torch.zeros((c.shape[0], 1, c.shape[2]), device=c.device)
+                    conds.append(c[0].t())                                   # [80, F] view; padded / copied per batch
     wavs = synthesize(model._generator, conds, max_batch=max_batch, max_frames=max_frames, group=group)
     if wavs is not None and int16:
         wavs = [wav_to_int16(w) for w in wavs]
