@@ -771,7 +771,7 @@ def test_packed_step_epilogue_is_bit_identical():
     pytest.param({"CUBE_TC_FUSED": "0", "CUBE_TC_CG2": "1"}, "student and tcgen05 and not full_length", id="student_cta_pair"),
     pytest.param({"CUBE_TC_WIN": "0"}, "hifigan and tcgen05 and not full_size and not loudness", id="hifigan_no_window"),
     pytest.param({"CUBE_TC_RBFUSE": "0"}, "hifigan and tcgen05 and not loudness", id="hifigan_unfused_resblock_steps"),
-    pytest.param({"CUBE_TC_WIDE": "0"}, "hifigan and tcgen05 and not loudness and not full_size", id="hifigan_one_subtile_128_stage"),
+    pytest.param({"CUBE_TC_WIDE": "2"}, "hifigan and tcgen05 and not loudness", id="hifigan_two_subtile_128_stage_forced"),
     pytest.param({"CUBE_RB_PK": "1"}, "hifigan and tcgen05 and not loudness", id="hifigan_packed_step_epilogue"),
     pytest.param({"CUBE_TC_LEAN": "0"}, "hifigan and tcgen05 and not loudness and not full_size", id="hifigan_generic_issue_loop"),
     pytest.param({"CUBE_TC_LEAN": "0"}, "student and tcgen05 and not full_length", id="student_generic_issue_loop"),

@@ -1073,15 +1073,17 @@ static int launch_rbstep(cube_voc* h, tc::RbParams& rp, cudaStream_t st) {
 }
 
 // WIDE variant of the 128-column tile (tc_conv.cuh, Cfg<.., MS>): two 128-row sub-tiles share every staged weight image.
-// For HiFi-GAN's 128-channel stage (-10 % per conv, profiles/r2n_*); CUBE_TC_WIDE=0/1 overrides the default
+// For HiFi-GAN's 128-channel stage (-10 % per conv, profiles/r2n_*); CUBE_TC_WIDE=0 / 1 / 2 overrides the default
 #ifndef CUBE_WIDE_DEFAULT
 #define CUBE_WIDE_DEFAULT 1   // B200 parity green (profiles/r2n_pytest_variants.log, r2p_pytest_lean.log); 128-channel stage -10 % per conv
 #endif
-static bool use_wide() {
+// 0 = never, 1 = where it pays (wide_pays), 2 = always (the parity suite forces it: its inputs are too small for the heuristic)
+static int wide_mode() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("CUBE_TC_WIDE"); v = e ? (e[0] == '1' ? 1 : 0) : CUBE_WIDE_DEFAULT; }
-  return v == 1;
+  if (v < 0) { const char* e = getenv("CUBE_TC_WIDE"); v = e ? (e[0] == '2' ? 2 : (e[0] == '1' ? 1 : 0)) : CUBE_WIDE_DEFAULT; }
+  return v;
 }
+static bool use_wide() { return wide_mode() > 0; }
 
 // tp.T = rows per batch item; fills t_tiles for the chosen variant and launches
 template <int TN, int MS = 0>
@@ -1157,9 +1159,18 @@ static void launch_tc_t(cube_voc* h, tc::TcParams& tp, cudaStream_t st) {
   tc::tc_conv_kernel<TN, false, false, MS><<<grid, tc::NUM_THREADS, tc::Cfg<TN, false, MS>::SMEM, st>>>(tp);
 }
 
+// Two sub-tiles per scheduled tile halve the number of tiles: worth it only while 128-row tiles would fill the SMs more than
+// twice over.  At batch 1 the 128-channel stage of a 10-s utterance has 108 such tiles for 148 SMs - as 54 double tiles every
+// conv of the stage would take twice as long (the latency the `api1` workload measures).
+static bool wide_pays(const cube_voc* h, const tc::TcParams& tp) {
+  const long long nph = tp.nphase > 0 ? tp.nphase : 1;
+  const long long tiles128 = (long long)tp.n_tiles * ((tp.T + tc::BM - 1) / tc::BM) * tp.B * nph;
+  return wide_mode() == 2 || tiles128 >= 2LL * h->sm_count;
+}
+
 static void launch_tc_bn(cube_voc* h, int bn, tc::TcParams& tp, cudaStream_t st) {
   if (bn == 256) launch_tc_t<256>(h, tp, st);
-  else if (bn == 128 && use_wide() && use_win(h) && !use_cg2()) launch_tc_t<128, 2>(h, tp, st);
+  else if (bn == 128 && use_wide() && use_win(h) && !use_cg2() && wide_pays(h, tp)) launch_tc_t<128, 2>(h, tp, st);
   else if (bn == 128) launch_tc_t<128>(h, tp, st);
   else if (bn == 64) launch_tc_t<64>(h, tp, st);
   else launch_tc_t<32>(h, tp, st);
