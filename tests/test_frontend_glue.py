@@ -230,3 +230,25 @@ def test_cubegan_inference_batch_uses_the_batched_frontend():
     for a, b in zip(batched, single):
         assert a.shape == b.shape and a.numel() > 0
         assert float((a - b).abs().max()) <= 1e-5
+
+
+def test_utterances_without_frames():
+    """Predicted durations all zero: the reference returns a [1, 0, 80] conditioning (``_expand_i`` on an empty alignment) and
+    ``Cubegan.inference`` replaces it by one zero frame (cube/networks/cubegan.py:78-80); the batched path returns [0, 80]."""
+    torch.manual_seed(2)
+    lang = TinyLanguasito().eval()
+    with torch.no_grad():                                   # the duration head always answers "0 frames"
+        lang._dur_output.linear_layer.weight.zero_()
+        lang._dur_output.linear_layer.bias.copy_(torch.tensor([5.0, 0, 0, 0, 0]))
+    xs, sp = _utterances(9, 3, 12)
+    got = FE.languasito_inference_batch(lang, xs, sp)
+    assert [tuple(g.shape) for g in got] == [(0, 80)] * 3
+    assert FR.languasito_inference(lang, xs[0][None], sp[0][None]).shape == (1, 0, 80)
+    # one silent utterance inside a batch of speaking ones: rows of the others are unaffected
+    with torch.no_grad():
+        lang._dur_output.linear_layer.bias.copy_(torch.tensor([0.0, 0, 5.0, 0, 0]))      # 2 frames per phone
+        lang._phon_emb_t.weight[3].zero_()
+    base = FE.languasito_inference_batch(lang, xs, sp)
+    assert [g.shape[0] for g in base] == [2 * x.numel() for x in xs]
+    import tts_cube_b200 as cube
+    assert cube.languasito_inference_batch is FE.languasito_inference_batch
