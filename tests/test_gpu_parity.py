@@ -772,9 +772,9 @@ def test_packed_step_epilogue_is_bit_identical():
     pytest.param({"CUBE_TC_WIN": "0"}, "hifigan and tcgen05 and not full_size and not loudness", id="hifigan_no_window"),
     pytest.param({"CUBE_TC_RBFUSE": "0"}, "hifigan and tcgen05 and not loudness", id="hifigan_unfused_resblock_steps"),
     pytest.param({"CUBE_TC_WIDE": "2"}, "hifigan and tcgen05 and not loudness", id="hifigan_two_subtile_128_stage_forced"),
-    pytest.param({"CUBE_RB_PK": "1"}, "hifigan and tcgen05 and not loudness", id="hifigan_packed_step_epilogue"),
+    pytest.param({"CUBE_RB_PK": "1"}, "hifigan and tcgen05 and not loudness and not full_size and not full_length", id="hifigan_packed_step_epilogue"),
     pytest.param({"CUBE_TC_LEAN": "0"}, "hifigan and tcgen05 and not loudness and not full_size", id="hifigan_generic_issue_loop"),
-    pytest.param({"CUBE_TC_LEAN": "0"}, "student and tcgen05 and not full_length", id="student_generic_issue_loop"),
+    pytest.param({"CUBE_TC_LEAN": "0"}, "student and tcgen05 and not full_length and not 862", id="student_generic_issue_loop"),
     pytest.param({"CUBE_TC_FP8": "0"}, "student and tcgen05", id="student_pair_fp16x3"),
     pytest.param({"CUBE_TC_AONCE": "1"}, "student and tcgen05", id="student_pair_a_once"),
     pytest.param({"CUBE_TC_AONCE": "1", "CUBE_TC_FP8": "0"}, "student and tcgen05 and not 862", id="student_pair_a_once_fp16x3"),
